@@ -1,0 +1,39 @@
+/*
+ * nerf_b200_debug.h -- test-only entry points of libnerf_b200.so (not part of the
+ * drop-in boundary; no reference counterpart). They expose host-side tables and saved
+ * intermediate panels so tests/ can check the fused MLP kernels layer by layer.
+ */
+#ifndef NERF_B200_DEBUG_H
+#define NERF_B200_DEBUG_H
+
+#include <stdint.h>
+
+#include "nerf_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Copy the per-tile program tables the fused MLP kernels execute for `cfg` (host only, no GPU
+ * needed). program: 0 = forward (training), 1 = forward (inference), 2 = backward dgrad chain.
+ * On entry *n_x holds the capacity of each array (in records), on exit the record count.
+ * info[0..9] = sizeof(MmaOp), sizeof(EpiJob), sizeof(PackChunk), sizeof(WgradUnit), packed weight
+ * bytes, activation slots, gradient slots, mask slots, padded bias floats, parameter count. */
+int nerf_debug_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *jobs, int32_t *n_jobs,
+                    void *chunks, int32_t *n_chunks, void *units, int32_t *n_units, int32_t *info);
+
+/* Padded-bias gather table: records of {uint32 dst_off; int64 src_base; int32 count, padded}. */
+int nerf_debug_plan_biases(const nerf_config *cfg, void *out, int32_t *n);
+
+/* Host-side pose matrices (rotateYaw 3x4, rotatePitch 3x3, src/ray_sampling.rs:20-69) and the
+ * screen offset tan(FOV/2)*HITHER the library feeds the sampler. No GPU needed. */
+int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3, float *off);
+
+/* Read one saved 16 KB panel image back: area 0 = activations, 1 = pre-activation gradients;
+ * area 2 = relu bit masks (slot = mask slot, out = 128*8 uint32). */
+int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slot, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

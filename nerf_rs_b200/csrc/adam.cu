@@ -1,0 +1,78 @@
+// adam.cu -- K-adam: one fused elementwise pass over the flat parameter blob.
+//
+// Restates nn::Adam::default() as used by Trainer::new/step (src/model.rs:306-309, :322):
+// betas (.9,.999), eps 1e-8, no weight decay, no amsgrad, in libtorch's op order
+//   m = m*b1 + g*(1-b1);  v = v*b2 + (1-b2)*g*g;
+//   denom = sqrt(v)/sqrt(1-b2^t) + eps;  p -= (lr/(1-b1^t)) * m/denom.
+// HBM-bound: p,m,v read+write, g read (+ zeroed for the next step) = 28(+4) B/param.
+// grad_scale folds the 1/nranks of the data-parallel all-reduce.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
+    const int64_t n4 = a.n >> 2;
+    const float omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = reinterpret_cast<float4 *>(a.p)[i];
+        float4 m = reinterpret_cast<float4 *>(a.m)[i];
+        float4 v = reinterpret_cast<float4 *>(a.v)[i];
+        float4 g = reinterpret_cast<float4 *>(a.g)[i];
+        float *pp = &p.x, *mm = &m.x, *vv = &v.x, *gg = &g.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gg[k] * a.grad_scale;
+            mm[k] = mm[k] * a.beta1 + gr * omb1;
+            vv[k] = vv[k] * a.beta2 + omb2 * gr * gr;
+            const float denom = sqrtf(vv[k]) * a.inv_sqrt_bc2 + a.eps;
+            pp[k] = pp[k] - a.lr_over_bc1 * (mm[k] / denom);
+        }
+        reinterpret_cast<float4 *>(a.p)[i] = p;
+        reinterpret_cast<float4 *>(a.m)[i] = m;
+        reinterpret_cast<float4 *>(a.v)[i] = v;
+        if (a.zero_grad) reinterpret_cast<float4 *>(a.g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < a.n; i += blockDim.x) {
+            const float gr = a.g[i] * a.grad_scale;
+            const float m = a.m[i] * a.beta1 + gr * omb1;
+            const float v = a.v[i] * a.beta2 + omb2 * gr * gr;
+            const float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;
+            a.p[i] = a.p[i] - a.lr_over_bc1 * (m / denom);
+            a.m[i] = m;
+            a.v[i] = v;
+            if (a.zero_grad) a.g[i] = 0.f;
+        }
+    }
+}
+
+// U(-1/sqrt(in), 1/sqrt(in)) for weights and biases -- the bound nn.Linear / tch nn::linear
+// defaults use (kaiming_uniform(a=sqrt(5)) reduces to it). Exact values are irrelevant once
+// set_weights injects a blob; this only makes a fresh context trainable.
+__global__ void k_init_uniform(float *p, LayerGeom lg, uint64_t seed, int layer) {
+    const int64_t nw = (int64_t)lg.in_dim * lg.out_dim;
+    const int64_t n = nw + lg.out_dim;
+    const float bound = rsqrtf((float)lg.in_dim);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float u = philox_uniform(seed, NERF_STREAM_INIT + (uint32_t)layer, (uint64_t)i);
+        const float val = (2.f * u - 1.f) * bound;
+        if (i < nw) p[lg.w_off + i] = val;
+        else p[lg.b_off + (i - nw)] = val;
+    }
+}
+
+}  // namespace
+
+void launch_adam(const AdamArgs &a, int num_sms, cudaStream_t st) {
+    int64_t n4 = a.n >> 2;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > num_sms * 8) blocks = num_sms * 8;
+    if (blocks < 1) blocks = 1;
+    k_adam<<<blocks, 256, 0, st>>>(a);
+}
+
+void launch_init_uniform(float *p, const NetGeom &g, uint64_t seed, cudaStream_t st) {
+    for (int l = 0; l < g.n_layers; ++l) k_init_uniform<<<64, 256, 0, st>>>(p, g.L[l], seed, l);
+}

@@ -1,0 +1,184 @@
+// composite.cu -- K-composite: front-to-back alpha compositing, one warp per ray.
+//
+// Forward restates src/model.rs:184-187 (deltas), :221-232 (transmittance) and
+// :234-249 (weights, weighted colour sum) as a segmented warp scan instead of the
+// reference's S separate slice/mul/sum/neg/exp chains:
+//   x_i = sigma_i * delta_i,  T_i = exp(-sum_{j<i} x_j),  w_i = T_i (1 - exp(-x_i)),
+//   out_c = sum_i w_i col_{i,c}.
+// Backward is the analytic gradient fused with the MSE gradient
+// g = 2 (out - gold) / (4R) of src/model.rs:296-299.
+// HBM-bound: 24 B/sample read forward; +20 B/sample written backward.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kMaxPerLane = 8;  // S <= 256
+
+__device__ __forceinline__ float warp_excl_scan_add(float v, int lane, float &total) {
+    float inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        float n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// Each lane owns a contiguous run of `spl` samples: i in [lane*spl, lane*spl+spl).
+template <bool kBackward>
+__global__ void __launch_bounds__(kWarps * 32)
+k_composite(CompositeArgs a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = a.num_samples;
+    const int spl = (S + 31) >> 5;
+    for (int r = blockIdx.x * kWarps + warp; r < a.num_rays; r += gridDim.x * kWarps) {
+        const float *sig = a.sigma + (size_t)r * S;
+        const float *tt = a.t_or_delta + (size_t)r * S;
+        const int i0 = lane * spl;
+        float x[kMaxPerLane], dl[kMaxPerLane], sg[kMaxPerLane];
+        float run = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int i = i0 + k;
+            x[k] = 0.f; dl[k] = 0.f; sg[k] = 0.f;
+            if (k < spl && i < S) {
+                float s = sig[i];
+                if (a.sigma_relu) s = fmaxf(s, 0.f);
+                float d;
+                if (a.input_is_delta) d = tt[i];
+                else d = ((i + 1 < S) ? tt[i + 1] : NERF_T_FAR) - tt[i];  // model.rs:184-187
+                sg[k] = s; dl[k] = d;
+                x[k] = s * d;
+                run += x[k];
+            }
+        }
+        float total;
+        float pre = warp_excl_scan_add(run, lane, total);  // sum_{j<i0} x_j
+
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        float w[kMaxPerLane], Tn[kMaxPerLane];
+        // accurate expf -- the reference uses ATen exp; keeps parity within 1e-6
+        float p = pre;
+        float col[kMaxPerLane][4];
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int i = i0 + k;
+            w[k] = 0.f; Tn[k] = 0.f;
+            col[k][0] = col[k][1] = col[k][2] = col[k][3] = 0.f;
+            if (k < spl && i < S) {
+                const float T = expf(-p);
+                const float av = expf(-x[k]);
+                w[k] = T * (1.f - av);       // model.rs:243
+                Tn[k] = T * av;              // T_{i+1}
+                if (a.colors) {
+                    const float4 c = reinterpret_cast<const float4 *>(a.colors)[(size_t)r * S + i];
+                    col[k][0] = c.x; col[k][1] = c.y; col[k][2] = c.z; col[k][3] = c.w;
+                } else {  // as shipped: colours (sigma,sigma,sigma,1) (model.rs:192-204)
+                    col[k][0] = sg[k]; col[k][1] = sg[k]; col[k][2] = sg[k]; col[k][3] = 1.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] += w[k] * col[k][c];
+                p += x[k];
+            }
+        }
+        float out[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) out[c] = warp_sum(acc[c]);  // model.rs:245-246
+
+        if (!kBackward) {
+            if (lane < 4) a.out[4 * (size_t)r + lane] = out[lane];
+            continue;
+        }
+
+        // ---- backward: g = dL/dout, either supplied or the fused MSE gradient
+        float g[4];
+        if (a.d_out) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g[c] = a.d_out[4 * (size_t)r + c];
+        } else {
+            float l = 0.f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float diff = out[c] - a.gold[4 * (size_t)r + c];
+                g[c] = 2.f * diff * a.inv_count;   // d mean((x-y)^2) / dx, count = 4R (model.rs:296-299)
+                l += diff * diff;
+            }
+            if (lane == 0 && a.ray_loss) a.ray_loss[r] = l;
+            if (lane < 4 && a.out) a.out[4 * (size_t)r + lane] = out[lane];
+        }
+        float ws[kMaxPerLane];
+        float runws = 0.f;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            ws[k] = 0.f;
+            if (k < spl && i0 + k < S) {
+                const float s = g[0] * col[k][0] + g[1] * col[k][1] + g[2] * col[k][2] + g[3] * col[k][3];
+                ws[k] = s;             // s_i
+                runws += w[k] * s;
+            }
+        }
+        float tot_ws;
+        float pre_ws = warp_excl_scan_add(runws, lane, tot_ws);
+        float incl = pre_ws;
+#pragma unroll
+        for (int k = 0; k < kMaxPerLane; ++k) {
+            const int i = i0 + k;
+            if (k < spl && i < S) {
+                incl += w[k] * ws[k];
+                const float suffix = tot_ws - incl;                   // sum_{k>i} w_k s_k
+                float dsig = dl[k] * (Tn[k] * ws[k] - suffix);        // dL/dsigma_i
+                if (a.colors) {
+                    float4 dc;
+                    dc.x = w[k] * g[0]; dc.y = w[k] * g[1]; dc.z = w[k] * g[2]; dc.w = w[k] * g[3];
+                    reinterpret_cast<float4 *>(a.d_colors)[(size_t)r * S + i] = dc;
+                } else {
+                    dsig += w[k] * (g[0] + g[1] + g[2]);              // direct colour = sigma terms
+                }
+                if (a.sigma_relu && sig[i] <= 0.f) dsig = 0.f;
+                a.d_sigma[(size_t)r * S + i] = dsig;
+            }
+        }
+    }
+}
+
+// deterministic fixed-order reduction of per-ray squared errors -> mean loss
+__global__ void k_loss_reduce(const float *__restrict__ ray_loss, int n, float inv_count, float *__restrict__ loss_out) {
+    __shared__ float sh[1024];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += ray_loss[i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = blockDim.x >> 1; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *loss_out = sh[0] * inv_count;
+}
+
+}  // namespace
+
+void launch_composite_fwd(const CompositeArgs &a, int num_sms, cudaStream_t st) {
+    int blocks = (a.num_rays + kWarps - 1) / kWarps;
+    int cap = num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_composite<false><<<blocks, kWarps * 32, 0, st>>>(a);
+}
+void launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st) {
+    int blocks = (a.num_rays + kWarps - 1) / kWarps;
+    int cap = num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_composite<true><<<blocks, kWarps * 32, 0, st>>>(a);
+}
+void launch_loss_reduce(const float *ray_loss, int n, float inv_count, float *loss_out, cudaStream_t st) {
+    k_loss_reduce<<<1, 1024, 0, st>>>(ray_loss, n, inv_count, loss_out);
+}

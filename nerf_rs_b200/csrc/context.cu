@@ -1,0 +1,1035 @@
+// context.cu -- implementation of the C ABI in include/nerf_b200.h.
+//
+// One nerf_ctx per GPU owns: the flat f32 parameter / gradient / Adam blobs, the resident
+// dataset (images + per-view pose matrices), the current ray batch, the MLP engine state
+// (tcgen05 chain kernels or the SIMT cross-check) and one CUDA stream on which everything
+// is enqueued. Call surface mirrors src/main.rs:57-72:
+//   get_multiview_batch -> NeRF::predict -> (compositing) -> Trainer::step.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/nerf_b200.h"
+#include "../../include/nerf_b200_debug.h"
+#include "comm.h"
+#include "kernels.h"
+#include "mlp_tc.h"
+
+namespace {
+
+struct Profiler {
+    bool on = false;
+    std::vector<std::string> names;
+    std::map<std::string, int> index;
+    struct Rec { int name; cudaEvent_t e0, e1; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    std::vector<double> total_ms;
+    std::vector<int> launches;
+    int open = -1;
+
+    cudaEvent_t get_event() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void begin(const char *name, cudaStream_t st) {
+        if (!on) return;
+        end(st);
+        auto it = index.find(name);
+        int id;
+        if (it == index.end()) {
+            id = (int)names.size();
+            names.push_back(name);
+            index[name] = id;
+            total_ms.push_back(0.0);
+            launches.push_back(0);
+        } else id = it->second;
+        Rec r{id, get_event(), get_event()};
+        cudaEventRecord(r.e0, st);
+        recs.push_back(r);
+        open = (int)recs.size() - 1;
+    }
+    void end(cudaStream_t st) {
+        if (!on || open < 0) return;
+        cudaEventRecord(recs[open].e1, st);
+        open = -1;
+    }
+    void collect(cudaStream_t st) {
+        end(st);
+        cudaStreamSynchronize(st);
+        for (auto &r : recs) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { total_ms[r.name] += ms; launches[r.name] += 1; }
+            pool.push_back(r.e0);
+            pool.push_back(r.e1);
+        }
+        recs.clear();
+    }
+    void reset() {
+        for (auto &t : total_ms) t = 0;
+        for (auto &l : launches) l = 0;
+    }
+};
+
+}  // namespace
+
+struct nerf_ctx {
+    nerf_config cfg;
+    NetGeom g;
+    int device = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launch_count = 0;
+    Profiler prof;
+
+    // parameters
+    float *d_params = nullptr, *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr;
+    int64_t step = 0;
+    bool weights_dirty = true;
+
+    // dataset
+    float *d_images = nullptr;
+    int n_img_views = 0;
+    ViewPose *d_poses = nullptr;
+    int n_poses = 0;
+    ViewPose *d_render_pose = nullptr;
+    float off = 0.f;
+
+    // batch
+    int R = 0, S = 0, chunk = 0;
+    int64_t B = 0;
+    int32_t *d_pix = nullptr, *d_view_pick = nullptr;
+    RayRec *d_rays = nullptr;
+    float *d_dirs = nullptr, *d_t = nullptr, *d_points = nullptr, *d_gold = nullptr, *d_jitter = nullptr;
+    float *d_sigma = nullptr, *d_rgba = nullptr, *d_out = nullptr, *d_dsigma = nullptr, *d_drgba = nullptr;
+    float *d_ray_loss = nullptr, *d_loss = nullptr;
+    float *h_loss = nullptr;   // pinned
+    int32_t *h_i32 = nullptr;  // pinned staging for index conversion
+    size_t h_i32_cap = 0;
+    bool batch_valid = false, predicted = false, acts_valid = false;
+
+    // engines
+    TcState *tc = nullptr;
+    SimtBuffers simt{};
+    bool simt_ready = false;
+
+    // comm
+    CommState comm;
+
+    // timers / scratch
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    uint8_t *d_flush = nullptr;
+    size_t flush_bytes = 0;
+};
+
+namespace {
+
+int fail(nerf_ctx *c, int code, const std::string &msg) {
+    if (c) c->err = msg;
+    return code;
+}
+#define CU(c, expr)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (expr);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(c, NERF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct Scope {
+    nerf_ctx *c;
+    Scope(nerf_ctx *c_, const char *name, int launches = 1) : c(c_) {
+        c->launch_count += launches;
+        c->prof.begin(name, c->stream);
+    }
+    ~Scope() { c->prof.end(c->stream); }
+};
+
+int check_launch(nerf_ctx *c, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(c, NERF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return NERF_OK;
+}
+
+void build_geom(const nerf_config &cfg, NetGeom &g) {
+    memset(&g, 0, sizeof(g));
+    g.W = cfg.hidden;
+    g.Wp = (cfg.hidden + 63) / 64 * 64;
+    g.W2 = cfg.hidden / 2;
+    g.W2p = (g.W2 + 63) / 64 * 64;
+    g.xyz_freqs = cfg.xyz_freqs;
+    g.dir_freqs = cfg.dir_freqs;
+    g.Cx = 3 + 6 * cfg.xyz_freqs;
+    g.Cd = cfg.dir_freqs < 0 ? 0 : 3 + 6 * cfg.dir_freqs;
+    g.skip_layer = cfg.skip_layer;
+    g.use_rgb_head = cfg.use_rgb_head;
+    g.sigma_relu = cfg.sigma_relu;
+    g.n_layers = 10;
+    int64_t off = 0;
+    for (int l = 1; l <= 10; ++l) {
+        int in, out;
+        if (l <= 7) {
+            in = (l == 1) ? g.Cx : g.W;
+            if (g.skip_layer && l == g.skip_layer + 1) in = g.W + g.Cx;
+            out = g.W;
+        } else if (l == 8) { in = g.W; out = g.W + 1; }   // sigma || features (model.rs:55)
+        else if (l == 9) { in = g.W + g.Cd; out = g.W2; } // model.rs:89
+        else { in = g.W2; out = 4; }                      // model.rs:90
+        g.L[l - 1].in_dim = in;
+        g.L[l - 1].out_dim = out;
+        g.L[l - 1].w_off = off;
+        off += (int64_t)in * out;
+        g.L[l - 1].b_off = off;
+        off += out;
+    }
+    g.n_params = off;
+}
+
+// rotateYaw / rotatePitch matrices (ray_sampling.rs:20-26, 32-69), built like the reference
+// builds them -- per call, in f32, libm cos/sin -- but once per view instead of once per point.
+void mat3_mul_rows(const float a[3][3], const float b[3][3], float o[3][3]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) o[i][j] = (a[i][0] * b[0][j] + a[i][1] * b[1][j]) + a[i][2] * b[2][j];
+}
+void make_pose(float yaw, float pitch, ViewPose &vp) {
+    memset(&vp, 0, sizeof(vp));
+    {
+        const float c = cosf(yaw), s = sinf(yaw);
+        const float m[3][4] = {{c, 0.f, s, 0.f}, {0.f, 1.f, 0.f, 0.f}, {-s, 0.f, c, 0.f}};
+        memcpy(vp.yaw, m, sizeof(m));
+    }
+    {
+        // v = normalize(AT - FROM) = (0,0,1); u = normalize(cross(v, UP))
+        const float at_from[3] = {0.f - 0.f, 0.f - 0.f, 1.f - (-1.f)};
+        const float inv = 1.f / sqrtf((at_from[0] * at_from[0] + at_from[1] * at_from[1]) + at_from[2] * at_from[2]);
+        const float v[3] = {at_from[0] * inv, at_from[1] * inv, at_from[2] * inv};
+        const float up[3] = {0.f, 1.f, 0.f};
+        const float cr[3] = {v[1] * up[2] - v[2] * up[1], v[2] * up[0] - v[0] * up[2], v[0] * up[1] - v[1] * up[0]};
+        const float inv2 = 1.f / sqrtf((cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2]);
+        const float ux = cr[0] * inv2, uy = cr[1] * inv2, uz = cr[2] * inv2;
+        const float cross_m[3][3] = {{0.f, -uz, uy}, {uz, 0.f, -ux}, {-uy, ux, 0.f}};
+        const float outer[3][3] = {{ux * ux, ux * uy, ux * uz}, {uy * ux, uy * uy, uy * uz}, {uz * ux, uz * uy, uz * uz}};
+        const float c = cosf(pitch), s = sinf(pitch);
+        const float idc[3][3] = {{c, 0.f, 0.f}, {0.f, c, 0.f}, {0.f, 0.f, c}};
+        const float ids[3][3] = {{s, 0.f, 0.f}, {0.f, s, 0.f}, {0.f, 0.f, s}};
+        float imc[3][3], cs[3][3], oc[3][3];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) imc[i][j] = (i == j ? 1.f : 0.f) - idc[i][j];
+        mat3_mul_rows(cross_m, ids, cs);
+        mat3_mul_rows(outer, imc, oc);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) vp.pitch[i][j] = (idc[i][j] + cs[i][j]) + oc[i][j];
+    }
+}
+
+float screen_offset() {
+    // tan(FOV/2) * HITHER evaluated at run time in f32 like f32::tan (ray_sampling.rs:80). The
+    // volatile keeps the compiler from folding it: tan(pi/6) sits within 1e-11 of an f32 rounding
+    // tie and a compile-time fold rounds the other way ("the tan(FOV/2) tie").
+    volatile float pi = 3.14159265358979323846f;
+    const float fov = pi / 3.f;
+    return tanf(fov / 2.f) * NERF_HITHER;
+}
+
+int ensure_i32(nerf_ctx *c, size_t n) {
+    if (c->h_i32_cap >= n) return NERF_OK;
+    if (c->h_i32) cudaFreeHost(c->h_i32);
+    c->h_i32 = nullptr;
+    c->h_i32_cap = 0;
+    CU(c, cudaMallocHost(&c->h_i32, n * sizeof(int32_t)));
+    c->h_i32_cap = n;
+    return NERF_OK;
+}
+
+void prof_between(void *user, const char *name) {
+    nerf_ctx *c = (nerf_ctx *)user;
+    if (name) { c->launch_count += 1; c->prof.begin(name, c->stream); }
+    else c->prof.end(c->stream);
+}
+
+int ensure_packed(nerf_ctx *c) {
+    if (c->weights_dirty && c->tc) {
+        Scope s(c, "pack_weights", 3);
+        tc_pack_weights(c->tc, c->d_params, c->stream);
+    }
+    c->weights_dirty = false;
+    return check_launch(c, "pack_weights");
+}
+
+// MLP forward on rays [r0, r0+nr) of the current batch
+int mlp_forward(nerf_ctx *c, int r0, int nr, int train) {
+    const int64_t n = (int64_t)nr * c->S;
+    const int64_t s0 = (int64_t)r0 * c->S;
+    if (c->cfg.mlp_impl == NERF_MLP_TCGEN05) {
+        int rc = ensure_packed(c);
+        if (rc) return rc;
+        Scope s(c, train ? "mlp_fwd_train" : "mlp_fwd");
+        if (tc_forward(c->tc, c->d_points + 3 * s0, c->d_dirs + 3 * (int64_t)r0, n, c->S, train, c->d_sigma + s0,
+                       c->d_rgba + 4 * s0, c->stream))
+            return fail(c, NERF_ERR_INVALID_ARG, tc_last_error(c->tc));
+    } else {
+        Scope s(c, "mlp_fwd_simt", 12);
+        simt_mlp_forward(c->g, c->d_params, c->d_points + 3 * s0, c->d_dirs + 3 * (int64_t)r0, nr, c->S,
+                         c->cfg.mlp_impl == NERF_MLP_SIMT ? 1 : 0, c->simt, c->d_sigma + s0, c->d_rgba + 4 * s0, c->stream);
+    }
+    return check_launch(c, "mlp_forward");
+}
+
+int mlp_backward(nerf_ctx *c, int r0, int nr) {
+    const int64_t n = (int64_t)nr * c->S;
+    const int64_t s0 = (int64_t)r0 * c->S;
+    if (c->cfg.mlp_impl == NERF_MLP_TCGEN05) {
+        if (tc_backward(c->tc, c->d_rgba + 4 * s0, c->d_dsigma + s0, c->d_drgba + 4 * s0, n, c->d_grads, c->stream,
+                        prof_between, c))
+            return fail(c, NERF_ERR_INVALID_ARG, tc_last_error(c->tc));
+    } else {
+        Scope s(c, "mlp_bwd_simt", 30);
+        simt_mlp_backward(c->g, c->d_params, c->d_grads, nr, c->S, c->cfg.mlp_impl == NERF_MLP_SIMT ? 1 : 0, c->simt,
+                          c->d_rgba + 4 * s0, c->d_dsigma + s0, c->d_drgba + 4 * s0, c->stream);
+    }
+    return check_launch(c, "mlp_backward");
+}
+
+int composite_forward(nerf_ctx *c, int nr, float *out) {
+    CompositeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sigma = c->d_sigma;
+    a.colors = c->cfg.use_rgb_head ? c->d_rgba : nullptr;
+    a.t_or_delta = c->d_t;
+    a.input_is_delta = 0;
+    a.sigma_relu = c->cfg.sigma_relu;
+    a.num_rays = nr;
+    a.num_samples = c->S;
+    a.out = out;
+    Scope s(c, "composite_fwd");
+    launch_composite_fwd(a, c->num_sms, c->stream);
+    return check_launch(c, "composite_fwd");
+}
+
+int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma) {
+    if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "predict: no batch (call nerf_get_batch or nerf_predict_points)");
+    c->acts_valid = false;
+    for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
+        const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
+        const int keep = train && c->chunk >= c->R;
+        int rc = mlp_forward(c, r0, nr, keep);
+        if (rc) return rc;
+        if (keep) c->acts_valid = true;
+    }
+    int rc = composite_forward(c, c->R, c->d_out);
+    if (rc) return rc;
+    c->predicted = true;
+    if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_out, sizeof(float) * 4 * c->R, cudaMemcpyDeviceToHost, c->stream));
+    if (out_sigma) CU(c, cudaMemcpyAsync(out_sigma, c->d_sigma, sizeof(float) * c->B, cudaMemcpyDeviceToHost, c->stream));
+    if (out_rgba || out_sigma) CU(c, cudaStreamSynchronize(c->stream));
+    return NERF_OK;
+}
+
+int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
+    if (!c->predicted) return fail(c, NERF_ERR_STATE, "step: predict has not run on this batch");
+    if (gold) {
+        if (n_gold != (int64_t)c->R * 4) return fail(c, NERF_ERR_INVALID_ARG, "step: gold must hold num_rays*4 floats (model.rs:316)");
+        CU(c, cudaMemcpyAsync(c->d_gold, gold, sizeof(float) * 4 * c->R, cudaMemcpyHostToDevice, c->stream));
+    }
+    const int nranks = c->comm.nranks;
+    {
+        CompositeArgs a;
+        memset(&a, 0, sizeof(a));
+        a.sigma = c->d_sigma;
+        a.colors = c->cfg.use_rgb_head ? c->d_rgba : nullptr;
+        a.t_or_delta = c->d_t;
+        a.sigma_relu = c->cfg.sigma_relu;
+        a.num_rays = c->R;
+        a.num_samples = c->S;
+        a.gold = c->d_gold;
+        a.inv_count = 1.f / (4.f * (float)c->R);   // mean over R*4 elements (model.rs:298)
+        a.ray_loss = c->d_ray_loss;
+        a.d_sigma = c->d_dsigma;
+        a.d_colors = c->d_drgba;
+        Scope s(c, "composite_bwd");
+        launch_composite_bwd(a, c->num_sms, c->stream);
+    }
+    {
+        Scope s(c, "loss_reduce");
+        launch_loss_reduce(c->d_ray_loss, c->R, 1.f / (4.f * (float)c->R), c->d_loss, c->stream);
+    }
+    int rc = check_launch(c, "composite_bwd");
+    if (rc) return rc;
+    // gradients accumulate (+=) over micro-batches and weight-gradient CTAs: start from zero
+    CU(c, cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->g.n_params, c->stream));
+    for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
+        const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
+        if (!c->acts_valid) {
+            rc = mlp_forward(c, r0, nr, 1);  // recompute this micro-batch's activations
+            if (rc) return rc;
+        }
+        rc = mlp_backward(c, r0, nr);
+        if (rc) return rc;
+    }
+    c->acts_valid = false;
+    c->predicted = false;
+    if (nranks > 1) {
+        Scope s(c, "grad_allreduce");
+        char eb[256] = {0};
+        if (comm_allreduce_sum_f32(c->comm, c->d_grads, c->g.n_params, c->stream, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
+    }
+    c->step += 1;
+    {
+        AdamArgs a;
+        a.p = c->d_params; a.m = c->d_m; a.v = c->d_v; a.g = c->d_grads;
+        a.n = c->g.n_params;
+        const double b1 = c->cfg.beta1, b2 = c->cfg.beta2;
+        const double bc1 = 1.0 - pow(b1, (double)c->step), bc2 = 1.0 - pow(b2, (double)c->step);
+        a.lr_over_bc1 = (float)((double)c->cfg.learning_rate / bc1);
+        a.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+        a.beta1 = c->cfg.beta1; a.beta2 = c->cfg.beta2; a.eps = c->cfg.eps;
+        a.grad_scale = 1.f / (float)nranks;
+        a.zero_grad = 0;
+        Scope s(c, "adam");
+        launch_adam(a, c->num_sms, c->stream);
+    }
+    c->weights_dirty = true;
+    rc = ensure_packed(c);
+    if (rc) return rc;
+    if (loss) {
+        CU(c, cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        float l = *c->h_loss;
+        *loss = l;
+    }
+    return check_launch(c, "step");
+}
+
+int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick, const ViewPose *poses, int fixed_view,
+                const float *jitter, int randomize, uint64_t seed, int64_t ray_base, bool gather_gold) {
+    SampleArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pix_yx = c->d_pix;
+    a.view_pick = view_pick;
+    a.rays_per_pick = rays_per_pick;
+    a.fixed_view = fixed_view;
+    a.poses = poses;
+    a.jitter = jitter;
+    a.images = gather_gold ? c->d_images : nullptr;
+    a.num_rays = nr;
+    a.num_samples = c->S;
+    a.img_w = c->cfg.image_w;
+    a.img_h = c->cfg.image_h;
+    a.randomize = randomize;
+    a.depth_mode = c->cfg.depth_mode;
+    a.off = c->off;
+    a.seed = seed;
+    a.ray_index_base = ray_base;
+    a.rays = c->d_rays;
+    a.dirs = c->d_dirs;
+    a.t = c->d_t;
+    a.points = c->d_points;
+    a.gold = c->d_gold;
+    Scope s(c, "sample");
+    launch_sample(a, c->num_sms, c->stream);
+    return check_launch(c, "sample");
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int nerf_abi_version(void) { return NERF_B200_ABI_VERSION; }
+
+int nerf_default_config(nerf_config *cfg) {
+    if (!cfg) return NERF_ERR_INVALID_ARG;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (int32_t)sizeof(nerf_config);
+    cfg->image_w = 800; cfg->image_h = 800;
+    cfg->num_rays = 4096; cfg->num_samples = 64;
+    cfg->hidden = 256; cfg->xyz_freqs = 10; cfg->dir_freqs = 4; cfg->skip_layer = 5;
+    cfg->use_rgb_head = 1; cfg->sigma_relu = 0;
+    cfg->depth_mode = NERF_DEPTH_REFERENCE;
+    cfg->mlp_impl = NERF_MLP_TCGEN05;
+    cfg->max_rays_per_launch = 0;
+    cfg->learning_rate = 5e-4f; cfg->beta1 = 0.9f; cfg->beta2 = 0.999f; cfg->eps = 1e-8f;
+    return NERF_OK;
+}
+
+int nerf_config_as_shipped(nerf_config *cfg) {
+    int rc = nerf_default_config(cfg);
+    if (rc) return rc;
+    cfg->image_w = 128; cfg->image_h = 128;       // ray_sampling.rs:7-8
+    cfg->num_rays = 84; cfg->num_samples = 64;    // model.rs:7-8
+    cfg->hidden = 100;                             // model.rs:12
+    cfg->xyz_freqs = 0; cfg->dir_freqs = -1; cfg->skip_layer = 0;
+    cfg->use_rgb_head = 0;                         // model.rs:190-206
+    return NERF_OK;
+}
+
+const char *nerf_strerror(int status) {
+    switch (status) {
+        case NERF_OK: return "ok";
+        case NERF_ERR_INVALID_ARG: return "invalid argument";
+        case NERF_ERR_CUDA: return "CUDA error";
+        case NERF_ERR_UNSUPPORTED: return "unsupported configuration";
+        case NERF_ERR_COMM: return "communication error";
+        case NERF_ERR_STATE: return "invalid call order";
+        case NERF_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+        default: return "unknown status";
+    }
+}
+
+const char *nerf_last_error(const nerf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int nerf_destroy(nerf_ctx *c) {
+    if (!c) return NERF_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    comm_destroy(c->comm);
+    tc_destroy(c->tc);
+    void *ptrs[] = {c->d_params, c->d_grads, c->d_m, c->d_v, c->d_images, c->d_poses, c->d_render_pose, c->d_pix, c->d_view_pick,
+                    c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
+                    c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
+                    c->d_flush};
+    for (void *p : ptrs) cudaFree(p);
+    if (c->h_loss) cudaFreeHost(c->h_loss);
+    if (c->h_i32) cudaFreeHost(c->h_i32);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    for (auto e : c->prof.pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NERF_OK;
+}
+
+int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
+    if (!cfg || !out) return NERF_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(nerf_config)) return NERF_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return NERF_ERR_NO_DEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NERF_ERR_NO_DEVICE;
+    if (prop.major != 10) return NERF_ERR_NO_DEVICE;  // kernels are built for sm_100a only
+    if (cfg->num_rays < 1 || cfg->num_samples < 1 || cfg->num_samples > 256 || cfg->hidden < 2 || cfg->hidden > 256 ||
+        cfg->xyz_freqs < 0 || cfg->xyz_freqs > 10 || cfg->dir_freqs > 4 || cfg->image_w < 1 || cfg->image_h < 1 ||
+        cfg->mlp_impl < 0 || cfg->mlp_impl > 2 || cfg->depth_mode < 0 || cfg->depth_mode > 1)
+        return NERF_ERR_UNSUPPORTED;
+    nerf_ctx *c = new nerf_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    build_geom(c->cfg, c->g);
+    c->R = cfg->num_rays;
+    c->S = cfg->num_samples;
+    c->B = (int64_t)c->R * c->S;
+    int64_t def_chunk = (int64_t)(1 << 21) / c->S;
+    if (def_chunk < 1) def_chunk = 1;
+    int64_t chunk = cfg->max_rays_per_launch > 0 ? cfg->max_rays_per_launch : def_chunk;
+    if (chunk > c->R) chunk = c->R;
+    c->chunk = (int)chunk;
+    c->off = screen_offset();
+
+    auto bail = [&](int code, const std::string &msg) {
+        fprintf(stderr, "nerf_create: %s\n", msg.c_str());
+        nerf_destroy(c);
+        return code;
+    };
+#define CUB(expr)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (expr);                                                                               \
+        if (e_ != cudaSuccess) return bail(NERF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+    CUB(cudaSetDevice(device));
+    CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUB(cudaEventCreate(&c->t0));
+    CUB(cudaEventCreate(&c->t1));
+    const int64_t P = c->g.n_params, Pp = (P + 3) / 4 * 4;
+    CUB(cudaMalloc(&c->d_params, sizeof(float) * Pp));
+    CUB(cudaMalloc(&c->d_grads, sizeof(float) * Pp));
+    CUB(cudaMalloc(&c->d_m, sizeof(float) * Pp));
+    CUB(cudaMalloc(&c->d_v, sizeof(float) * Pp));
+    CUB(cudaMemsetAsync(c->d_params, 0, sizeof(float) * Pp, c->stream));
+    CUB(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * Pp, c->stream));
+    CUB(cudaMemsetAsync(c->d_m, 0, sizeof(float) * Pp, c->stream));
+    CUB(cudaMemsetAsync(c->d_v, 0, sizeof(float) * Pp, c->stream));
+    const int64_t R = c->R, B = c->B;
+    CUB(cudaMalloc(&c->d_pix, sizeof(int32_t) * 2 * R));
+    CUB(cudaMalloc(&c->d_view_pick, sizeof(int32_t) * R));
+    CUB(cudaMalloc(&c->d_rays, sizeof(RayRec) * R));
+    CUB(cudaMalloc(&c->d_dirs, sizeof(float) * 3 * R));
+    CUB(cudaMalloc(&c->d_t, sizeof(float) * B));
+    CUB(cudaMalloc(&c->d_points, sizeof(float) * 3 * B));
+    CUB(cudaMalloc(&c->d_gold, sizeof(float) * 4 * R));
+    CUB(cudaMalloc(&c->d_jitter, sizeof(float) * B));
+    CUB(cudaMalloc(&c->d_sigma, sizeof(float) * B));
+    CUB(cudaMalloc(&c->d_rgba, sizeof(float) * 4 * B));
+    CUB(cudaMalloc(&c->d_out, sizeof(float) * 4 * R));
+    CUB(cudaMalloc(&c->d_dsigma, sizeof(float) * B));
+    CUB(cudaMalloc(&c->d_drgba, sizeof(float) * 4 * B));
+    CUB(cudaMalloc(&c->d_ray_loss, sizeof(float) * R));
+    CUB(cudaMalloc(&c->d_loss, sizeof(float) * 4));
+    CUB(cudaMalloc(&c->d_render_pose, sizeof(ViewPose)));
+    CUB(cudaMemsetAsync(c->d_gold, 0, sizeof(float) * 4 * R, c->stream));
+    CUB(cudaMemsetAsync(c->d_rgba, 0, sizeof(float) * 4 * B, c->stream));
+    CUB(cudaMemsetAsync(c->d_drgba, 0, sizeof(float) * 4 * B, c->stream));
+    CUB(cudaMemsetAsync(c->d_loss, 0, sizeof(float) * 4, c->stream));
+    CUB(cudaMallocHost(&c->h_loss, sizeof(float) * 4));
+    if (cfg->mlp_impl == NERF_MLP_TCGEN05) {
+        std::string e;
+        const int64_t max_tiles = ((int64_t)c->chunk * c->S + NERF_TILE_M - 1) / NERF_TILE_M;
+        c->tc = tc_create(c->g, max_tiles, c->num_sms, e);
+        if (!c->tc) return bail(NERF_ERR_UNSUPPORTED, e);
+    } else {
+        const int64_t bc = (int64_t)c->chunk * c->S;
+        c->simt.act_stride = bc * (int64_t)simt_act_floats_per_sample(c->g);
+        CUB(cudaMalloc(&c->simt.x_enc, sizeof(float) * bc * c->g.Cx));
+        CUB(cudaMalloc(&c->simt.d_enc, sizeof(float) * (int64_t)c->chunk * (c->g.Cd > 0 ? c->g.Cd : 1)));
+        CUB(cudaMalloc(&c->simt.act, sizeof(float) * c->simt.act_stride * 9));
+        CUB(cudaMalloc(&c->simt.dact, sizeof(float) * c->simt.act_stride * 3));
+        c->simt_ready = true;
+    }
+#undef CUB
+    launch_init_uniform(c->d_params, c->g, 0x5eed5eedull, c->stream);
+    c->launch_count += 10;
+    c->weights_dirty = true;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess)
+        return bail(NERF_ERR_CUDA, "initialisation kernels failed");
+    *out = c;
+    return NERF_OK;
+}
+
+int64_t nerf_num_params(const nerf_ctx *c) { return c ? c->g.n_params : 0; }
+int64_t nerf_launch_count(const nerf_ctx *c) { return c ? c->launch_count : 0; }
+
+int nerf_set_weights(nerf_ctx *c, const float *flat, int64_t n) {
+    if (!c || !flat) return NERF_ERR_INVALID_ARG;
+    if (n != c->g.n_params) return fail(c, NERF_ERR_INVALID_ARG, "set_weights: wrong parameter count");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(c->d_params, flat, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->weights_dirty = true;
+    return NERF_OK;
+}
+static int get_blob(nerf_ctx *c, const float *src, float *dst, int64_t n) {
+    if (!c || !dst) return NERF_ERR_INVALID_ARG;
+    if (n != c->g.n_params) return fail(c, NERF_ERR_INVALID_ARG, "wrong parameter count");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NERF_OK;
+}
+int nerf_get_weights(nerf_ctx *c, float *flat, int64_t n) { return get_blob(c, c ? c->d_params : nullptr, flat, n); }
+int nerf_get_grads(nerf_ctx *c, float *flat, int64_t n) { return get_blob(c, c ? c->d_grads : nullptr, flat, n); }
+int nerf_get_adam_state(nerf_ctx *c, float *m, float *v, int64_t n, int64_t *step) {
+    int rc = get_blob(c, c ? c->d_m : nullptr, m, n);
+    if (rc) return rc;
+    rc = get_blob(c, c->d_v, v, n);
+    if (rc) return rc;
+    if (step) *step = c->step;
+    return NERF_OK;
+}
+int nerf_set_adam_state(nerf_ctx *c, const float *m, const float *v, int64_t n, int64_t step) {
+    if (!c || !m || !v || step < 0) return NERF_ERR_INVALID_ARG;
+    if (n != c->g.n_params) return fail(c, NERF_ERR_INVALID_ARG, "set_adam_state: wrong parameter count");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(c->d_m, m, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_v, v, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->step = step;
+    return NERF_OK;
+}
+
+int nerf_set_images(nerf_ctx *c, const float *rgba, int32_t n_views) {
+    if (!c || !rgba || n_views < 1) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(float) * 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
+    if (c->d_images) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_images); c->d_images = nullptr; }
+    CU(c, cudaMalloc(&c->d_images, bytes));
+    CU(c, cudaMemcpyAsync(c->d_images, rgba, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_img_views = n_views;
+    return NERF_OK;
+}
+
+int nerf_set_view_angles(nerf_ctx *c, const float *yaw_pitch, int32_t n) {
+    if (!c || !yaw_pitch || n < 1) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    std::vector<ViewPose> poses((size_t)n);
+    for (int i = 0; i < n; ++i) make_pose(yaw_pitch[2 * i], yaw_pitch[2 * i + 1], poses[i]);
+    if (c->d_poses) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_poses); c->d_poses = nullptr; }
+    CU(c, cudaMalloc(&c->d_poses, sizeof(ViewPose) * (size_t)n));
+    CU(c, cudaMemcpyAsync(c->d_poses, poses.data(), sizeof(ViewPose) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_poses = n;
+    return NERF_OK;
+}
+
+int nerf_view_angles_grid(int32_t nv, float *out, int32_t capacity) {
+    // image_loading.rs:67-80: yaw advances once per outer step, pitch per inner step, both by
+    // repeated f32 addition of pi/n; 2n(n+1) pairs.
+    if (nv < 1 || !out || capacity < 2 * nv * (nv + 1)) return NERF_ERR_INVALID_ARG;
+    const float pi = 3.14159265358979323846f;
+    float rot_ver = 0.f, rot_hor = 0.f;
+    int k = 0;
+    for (int i = 0; i < 2 * nv; ++i) {
+        for (int j = 0; j < nv + 1; ++j) {
+            out[2 * k] = rot_hor;
+            out[2 * k + 1] = rot_ver;
+            ++k;
+            rot_ver = rot_ver + pi / (float)nv;
+        }
+        rot_hor = rot_hor + pi / (float)nv;
+        rot_ver = 0.f;
+    }
+    return NERF_OK;
+}
+
+int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_index, int32_t n_picks, const float *jitter,
+                   int32_t randomize, uint64_t seed, float *out_points, float *out_t, float *out_gold, float *out_dirs,
+                   int64_t *out_indices) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (!c->d_poses) return fail(c, NERF_ERR_STATE, "get_batch: call nerf_set_view_angles first");
+    const int R = c->R, S = c->S;
+    if (n_picks < 1 || n_picks > R || R % n_picks != 0)
+        return fail(c, NERF_ERR_INVALID_ARG, "get_batch: can't divide rays evenly among views (dataset.rs:73-81)");
+    const int n_views = (c->d_images && c->n_img_views < c->n_poses) ? c->n_img_views : c->n_poses;
+    int rc;
+    if (indices_yx) {
+        rc = ensure_i32(c, (size_t)2 * R + n_picks);
+        if (rc) return rc;
+        for (int i = 0; i < R; ++i) {
+            const int64_t y = indices_yx[2 * i], x = indices_yx[2 * i + 1];
+            if (y < 0 || y >= c->cfg.image_h || x < 0 || x >= c->cfg.image_w) return fail(c, NERF_ERR_INVALID_ARG, "get_batch: pixel index out of range");
+            c->h_i32[2 * i] = (int32_t)y;
+            c->h_i32[2 * i + 1] = (int32_t)x;
+        }
+        CU(c, cudaMemcpyAsync(c->d_pix, c->h_i32, sizeof(int32_t) * 2 * R, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (view_index) {
+        rc = ensure_i32(c, (size_t)2 * R + n_picks);
+        if (rc) return rc;
+        for (int i = 0; i < n_picks; ++i) {
+            if (view_index[i] < 0 || view_index[i] >= n_views) return fail(c, NERF_ERR_INVALID_ARG, "get_batch: view index out of range");
+            c->h_i32[2 * R + i] = (int32_t)view_index[i];
+        }
+        CU(c, cudaMemcpyAsync(c->d_view_pick, c->h_i32 + 2 * R, sizeof(int32_t) * n_picks, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (!indices_yx || !view_index) {
+        Scope s(c, "pick");
+        launch_pick(c->d_pix, c->d_view_pick, R, n_picks, n_views, c->cfg.image_w, c->cfg.image_h, seed, indices_yx ? 0 : 1,
+                    view_index ? 0 : 1, c->stream);
+    }
+    const float *dj = nullptr;
+    if (jitter && randomize) {
+        CU(c, cudaMemcpyAsync(c->d_jitter, jitter, sizeof(float) * (size_t)R * S, cudaMemcpyHostToDevice, c->stream));
+        dj = c->d_jitter;
+    }
+    const int64_t ray_base = (int64_t)c->comm.rank * R;
+    rc = run_sampler(c, R, c->d_view_pick, R / n_picks, c->d_poses, 0, dj, randomize, seed, ray_base, c->d_images != nullptr);
+    if (rc) return rc;
+    c->batch_valid = true;
+    c->predicted = false;
+    c->acts_valid = false;
+    bool sync = false;
+    if (out_points) { CU(c, cudaMemcpyAsync(out_points, c->d_points, sizeof(float) * 3 * c->B, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
+    if (out_t) { CU(c, cudaMemcpyAsync(out_t, c->d_t, sizeof(float) * c->B, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
+    if (out_gold) { CU(c, cudaMemcpyAsync(out_gold, c->d_gold, sizeof(float) * 4 * R, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
+    if (out_dirs) { CU(c, cudaMemcpyAsync(out_dirs, c->d_dirs, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
+    if (out_indices) {
+        rc = ensure_i32(c, (size_t)2 * R + n_picks);
+        if (rc) return rc;
+        CU(c, cudaMemcpyAsync(c->h_i32, c->d_pix, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+        sync = true;
+    }
+    if (sync) CU(c, cudaStreamSynchronize(c->stream));
+    if (out_indices) for (int i = 0; i < 2 * R; ++i) out_indices[i] = c->h_i32[i];
+    return check_launch(c, "get_batch");
+}
+
+int nerf_predict(nerf_ctx *c, int32_t train, float *out_rgba, float *out_sigma) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    return do_predict(c, train, out_rgba, out_sigma);
+}
+
+int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points_floats, const float *distances,
+                        int64_t n_distances, const float *dirs, int32_t train, float *out_rgba, float *out_sigma) {
+    if (!c || !query_points || !distances) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    // assert_eq!(query_points.size(), [BATCH_SIZE*INDIM]); assert_eq!(distances.size(), [BATCH_SIZE]) (model.rs:162-163)
+    if (n_points_floats != c->B * 3) return fail(c, NERF_ERR_INVALID_ARG, "predict: query_points must hold num_rays*num_samples*3 floats (model.rs:162)");
+    if (n_distances != c->B) return fail(c, NERF_ERR_INVALID_ARG, "predict: distances must hold num_rays*num_samples floats (model.rs:163)");
+    if (c->g.Cd && !dirs) return fail(c, NERF_ERR_INVALID_ARG, "predict: this configuration needs ray directions [num_rays*3]");
+    CU(c, cudaMemcpyAsync(c->d_points, query_points, sizeof(float) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->stream));
+    if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->stream));
+    c->batch_valid = true;
+    c->predicted = false;
+    return do_predict(c, train, out_rgba, out_sigma);
+}
+
+int nerf_compositing(nerf_ctx *c, const float *densities, const float *colors, const float *distances, int32_t num_rays,
+                     int32_t num_samples, float *out) {
+    if (!c || !densities || !distances || !out) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (num_rays < 1 || num_samples < 1 || num_samples > 256) return fail(c, NERF_ERR_INVALID_ARG, "compositing: bad shape");
+    const size_t n = (size_t)num_rays * num_samples;
+    float *ds = nullptr, *dc = nullptr, *dd = nullptr, *dout = nullptr;
+    CU(c, cudaMalloc(&ds, sizeof(float) * n));
+    CU(c, cudaMalloc(&dd, sizeof(float) * n));
+    CU(c, cudaMalloc(&dout, sizeof(float) * 4 * num_rays));
+    if (colors) CU(c, cudaMalloc(&dc, sizeof(float) * 4 * n));
+    CU(c, cudaMemcpyAsync(ds, densities, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(dd, distances, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
+    if (colors) CU(c, cudaMemcpyAsync(dc, colors, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, c->stream));
+    CompositeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.sigma = ds; a.colors = dc; a.t_or_delta = dd; a.input_is_delta = 1; a.sigma_relu = 0;
+    a.num_rays = num_rays; a.num_samples = num_samples; a.out = dout;
+    {
+        Scope s(c, "composite_fwd");
+        launch_composite_fwd(a, c->num_sms, c->stream);
+    }
+    CU(c, cudaMemcpyAsync(out, dout, sizeof(float) * 4 * num_rays, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    cudaFree(ds); cudaFree(dd); cudaFree(dout); cudaFree(dc);
+    return check_launch(c, "compositing");
+}
+
+int nerf_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    return do_step(c, gold, n_gold, loss);
+}
+
+int nerf_train_iter(nerf_ctx *c, uint64_t seed) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (!c->d_images) return fail(c, NERF_ERR_STATE, "train_iter: call nerf_set_images first");
+    int n_picks = c->n_img_views < c->n_poses ? c->n_img_views : c->n_poses;
+    while (n_picks > 1 && c->R % n_picks != 0) --n_picks;   // largest pick count that splits R evenly
+    int rc = nerf_get_batch(c, nullptr, nullptr, n_picks, nullptr, 1, seed, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    rc = do_predict(c, 1, nullptr, nullptr);
+    if (rc) return rc;
+    return do_step(c, nullptr, 0, nullptr);
+}
+
+int nerf_last_loss(nerf_ctx *c, float *loss) {
+    if (!c || !loss) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *loss = *c->h_loss;
+    return NERF_OK;
+}
+
+int nerf_sync(nerf_ctx *c) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "sync");
+}
+
+int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed, float *out_rgba,
+                uint32_t *out_0rgb) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int W = c->cfg.image_w, H = c->cfg.image_h;
+    if (y0 < 0 || y1 > H || y0 >= y1) return fail(c, NERF_ERR_INVALID_ARG, "render: bad row range");
+    ViewPose vp;
+    make_pose(yaw, pitch, vp);
+    CU(c, cudaMemcpyAsync(c->d_render_pose, &vp, sizeof(vp), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));  // vp is a stack temporary
+    const int64_t total = (int64_t)(y1 - y0) * W;
+    uint32_t *d_packed = nullptr;
+    if (out_0rgb) CU(c, cudaMalloc(&d_packed, sizeof(uint32_t) * (size_t)c->R));
+    c->batch_valid = false;
+    c->predicted = false;
+    c->acts_valid = false;
+    const int saveR = c->R;
+    int rc = NERF_OK;
+    for (int64_t p0 = 0; p0 < total && rc == NERF_OK; p0 += saveR) {
+        const int nr = (int)((total - p0 < saveR) ? total - p0 : saveR);
+        // pixel (y,x) list of this chunk, row-major (display.rs:58-62)
+        {
+            Scope s(c, "frame_indices");
+            // indices for flat pixel range [p0, p0+nr): reuse the full-frame kernel on whole rows when aligned
+            const int ya = y0 + (int)(p0 / W), yb = y0 + (int)((p0 + nr + W - 1) / W);
+            if (p0 % W == 0 && (int64_t)(yb - ya) * W <= saveR) {
+                launch_full_frame_indices(c->d_pix, ya, yb, W, c->stream);
+            } else {
+                rc = ensure_i32(c, (size_t)2 * saveR + 1);
+                if (rc) break;
+                for (int i = 0; i < nr; ++i) {
+                    c->h_i32[2 * i] = y0 + (int)((p0 + i) / W);
+                    c->h_i32[2 * i + 1] = (int)((p0 + i) % W);
+                }
+                cudaMemcpyAsync(c->d_pix, c->h_i32, sizeof(int32_t) * 2 * nr, cudaMemcpyHostToDevice, c->stream);
+                cudaStreamSynchronize(c->stream);
+            }
+        }
+        rc = run_sampler(c, nr, nullptr, 1, c->d_render_pose, 0, nullptr, randomize, seed, p0, false);
+        if (rc) break;
+        c->R = nr;  // temporarily narrow the batch view for the engines
+        for (int r0 = 0; r0 < nr && rc == NERF_OK; r0 += c->chunk) {
+            const int n2 = (nr - r0 < c->chunk) ? nr - r0 : c->chunk;
+            rc = mlp_forward(c, r0, n2, 0);
+        }
+        if (rc == NERF_OK) rc = composite_forward(c, nr, c->d_out);
+        c->R = saveR;
+        if (rc) break;
+        if (out_rgba) cudaMemcpyAsync(out_rgba + 4 * p0, c->d_out, sizeof(float) * 4 * nr, cudaMemcpyDeviceToHost, c->stream);
+        if (out_0rgb) {
+            Scope s(c, "pack_0rgb");
+            launch_pack_0rgb(c->d_out, d_packed, nr, c->stream);
+            cudaMemcpyAsync(out_0rgb + p0, d_packed, sizeof(uint32_t) * nr, cudaMemcpyDeviceToHost, c->stream);
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (d_packed) cudaFree(d_packed);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(c, NERF_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    return check_launch(c, "render");
+}
+
+int nerf_comm_unique_id(void *id128) {
+    if (!id128) return NERF_ERR_INVALID_ARG;
+    char eb[256] = {0};
+    if (comm_unique_id(id128, eb, sizeof(eb))) {
+        fprintf(stderr, "nerf_comm_unique_id: %s\n", eb);
+        return NERF_ERR_COMM;
+    }
+    return NERF_OK;
+}
+
+int nerf_comm_init_rank(nerf_ctx *c, const void *id128, int32_t rank, int32_t nranks) {
+    if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    char eb[256] = {0};
+    if (comm_init_rank(c->comm, id128, rank, nranks, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
+    return NERF_OK;
+}
+
+int nerf_comm_destroy(nerf_ctx *c) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    comm_destroy(c->comm);
+    return NERF_OK;
+}
+
+int nerf_timer_start(nerf_ctx *c) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->t0, c->stream));
+    return NERF_OK;
+}
+int nerf_timer_stop(nerf_ctx *c, float *ms) {
+    if (!c || !ms) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaEventRecord(c->t1, c->stream));
+    CU(c, cudaEventSynchronize(c->t1));
+    CU(c, cudaEventElapsedTime(ms, c->t0, c->t1));
+    return check_launch(c, "timer_stop");
+}
+
+int nerf_profile_enable(nerf_ctx *c, int32_t on) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    c->prof.collect(c->stream);
+    c->prof.reset();
+    c->prof.on = on != 0;
+    return NERF_OK;
+}
+int nerf_profile_read(nerf_ctx *c, char *names, float *total_ms, int32_t *launches, int32_t capacity, int32_t *count) {
+    if (!c || !count) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    c->prof.collect(c->stream);
+    const int n = (int)c->prof.names.size();
+    *count = n;
+    for (int i = 0; i < n && i < capacity; ++i) {
+        if (names) { strncpy(names + 32 * i, c->prof.names[i].c_str(), 31); names[32 * i + 31] = 0; }
+        if (total_ms) total_ms[i] = (float)c->prof.total_ms[i];
+        if (launches) launches[i] = c->prof.launches[i];
+    }
+    return NERF_OK;
+}
+
+int nerf_flush_l2(nerf_ctx *c) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (!c->d_flush) {
+        c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+        CU(c, cudaMalloc(&c->d_flush, c->flush_bytes));
+    }
+    CU(c, cudaMemsetAsync(c->d_flush, (int)(c->launch_count & 0xff), c->flush_bytes, c->stream));
+    return NERF_OK;
+}
+
+// ------------------------------------------------------------------------------- debug
+int nerf_debug_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *jobs, int32_t *n_jobs, void *chunks,
+                    int32_t *n_chunks, void *units, int32_t *n_units, int32_t *info) {
+    if (!cfg) return NERF_ERR_INVALID_ARG;
+    NetGeom g;
+    build_geom(*cfg, g);
+    TcPlan plan;
+    std::string err;
+    if (!tc_build_plan(g, plan, err)) {
+        fprintf(stderr, "nerf_debug_plan: %s\n", err.c_str());
+        return NERF_ERR_UNSUPPORTED;
+    }
+    const TcProgram &P = program == 0 ? plan.fwd_train : (program == 1 ? plan.fwd_infer : plan.bwd);
+    if (ops && n_ops && *n_ops >= (int)P.ops.size()) memcpy(ops, P.ops.data(), P.ops.size() * sizeof(MmaOp));
+    if (jobs && n_jobs && *n_jobs >= (int)P.jobs.size()) memcpy(jobs, P.jobs.data(), P.jobs.size() * sizeof(EpiJob));
+    if (chunks && n_chunks && *n_chunks >= (int)P.chunks.size()) memcpy(chunks, P.chunks.data(), P.chunks.size() * sizeof(PackChunk));
+    if (units && n_units && *n_units >= (int)plan.units.size()) memcpy(units, plan.units.data(), plan.units.size() * sizeof(WgradUnit));
+    if (n_ops) *n_ops = (int)P.ops.size();
+    if (n_jobs) *n_jobs = (int)P.jobs.size();
+    if (n_chunks) *n_chunks = (int)P.chunks.size();
+    if (n_units) *n_units = (int)plan.units.size();
+    if (info) {
+        info[0] = (int)sizeof(MmaOp); info[1] = (int)sizeof(EpiJob); info[2] = (int)sizeof(PackChunk); info[3] = (int)sizeof(WgradUnit);
+        info[4] = (int)P.wpack_bytes; info[5] = plan.act_slots; info[6] = plan.grad_slots; info[7] = plan.mask_slots;
+        info[8] = (int)plan.bias_floats; info[9] = (int)g.n_params;
+    }
+    return NERF_OK;
+}
+
+int nerf_debug_plan_biases(const nerf_config *cfg, void *out, int32_t *n) {
+    if (!cfg || !n) return NERF_ERR_INVALID_ARG;
+    NetGeom g;
+    build_geom(*cfg, g);
+    TcPlan plan;
+    std::string err;
+    if (!tc_build_plan(g, plan, err)) return NERF_ERR_UNSUPPORTED;
+    if (out && *n >= (int)plan.biases.size()) memcpy(out, plan.biases.data(), plan.biases.size() * sizeof(PackBias));
+    *n = (int)plan.biases.size();
+    return NERF_OK;
+}
+
+int nerf_debug_read_panel(nerf_ctx *c, int32_t area, int32_t tile, int32_t slot, void *out) {
+    if (!c || !out) return NERF_ERR_INVALID_ARG;
+    if (!c->tc) return fail(c, NERF_ERR_STATE, "debug_read_panel: not a tcgen05 context");
+    CU(c, cudaSetDevice(c->device));
+    const int rc = tc_debug_read(c->tc, area, tile, slot, out, c->stream);
+    if (rc == -1) return fail(c, NERF_ERR_INVALID_ARG, "debug_read_panel: bad area/tile/slot");
+    if (rc) return fail(c, NERF_ERR_CUDA, "debug_read_panel: copy failed");
+    return NERF_OK;
+}
+
+int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3, float *off) {
+    ViewPose vp;
+    make_pose(yaw, pitch, vp);
+    if (yaw3x4) memcpy(yaw3x4, vp.yaw, sizeof(vp.yaw));
+    if (pitch3x3) memcpy(pitch3x3, vp.pitch, sizeof(vp.pitch));
+    if (off) *off = screen_offset();
+    return NERF_OK;
+}
+
+}  // extern "C"

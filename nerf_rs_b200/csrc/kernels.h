@@ -1,0 +1,78 @@
+// kernels.h -- launcher declarations shared by the kernel translation units and the context.
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------- sampling.cu
+struct SampleArgs {
+    const int32_t *pix_yx;     // [R][2] (y, x)
+    const int32_t *view_pick;  // [n_picks] view ids, ray r uses view_pick[r / rays_per_pick]; NULL -> fixed_view
+    int32_t rays_per_pick, fixed_view;
+    const ViewPose *poses;
+    const float *jitter;       // [R][S] or NULL -> Philox
+    const float *images;       // [V][H*W][4] or NULL
+    int32_t num_rays, num_samples, img_w, img_h;
+    int32_t randomize, depth_mode;
+    float off;                 // tan(FOV/2) * HITHER, from the host
+    uint64_t seed;
+    int64_t ray_index_base;    // global ray offset for the Philox jitter counter (rank / micro-batch)
+    RayRec *rays;              // [R]
+    float *dirs;               // [R][3]
+    float *t;                  // [R][S]
+    float *points;             // [R][S][3] or NULL
+    float *gold;               // [R][4]
+};
+void launch_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks, int n_views, int img_w, int img_h,
+                 uint64_t seed, int gen_pix, int gen_view, cudaStream_t st);
+void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st);
+void launch_encode(const float *x, float *out, int64_t n, int freqs, int repeat, cudaStream_t st);
+void launch_pack_0rgb(const float *rgba, uint32_t *out, int64_t n, cudaStream_t st);
+void launch_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w, cudaStream_t st);
+
+// ---------------------------------------------------------------- composite.cu
+struct CompositeArgs {
+    const float *sigma;        // [R][S]
+    const float *colors;       // [R][S][4] or NULL -> (sigma,sigma,sigma,1)
+    const float *t_or_delta;   // [R][S]
+    int32_t input_is_delta;    // 1: deltas (standalone reference signature); 0: t values, deltas fused
+    int32_t sigma_relu;
+    int32_t num_rays, num_samples;
+    float *out;                // [R][4]
+    // backward
+    const float *gold;         // [R][4] (fused MSE) -- used when d_out == NULL
+    const float *d_out;        // [R][4] explicit upstream gradient or NULL
+    float inv_count;           // 1 / (4 R_total)
+    float *ray_loss;           // [R] per-ray sum of squared errors
+    float *d_sigma;            // [R][S]
+    float *d_colors;           // [R][S][4]
+};
+void launch_composite_fwd(const CompositeArgs &a, int num_sms, cudaStream_t st);
+void launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st);
+void launch_loss_reduce(const float *ray_loss, int n, float inv_count, float *loss_out, cudaStream_t st);
+
+// ---------------------------------------------------------------- adam.cu
+struct AdamArgs {
+    float *p, *m, *v, *g;
+    int64_t n;
+    float lr_over_bc1, inv_sqrt_bc2, beta1, beta2, eps, grad_scale;
+    int32_t zero_grad;
+};
+void launch_adam(const AdamArgs &a, int num_sms, cudaStream_t st);
+void launch_init_uniform(float *p, const NetGeom &g, uint64_t seed, cudaStream_t st);
+
+// ---------------------------------------------------------------- mlp_simt.cu
+// Plain CUDA-core MLP (forward + backward) used as an on-device cross-check of the
+// tcgen05 path. round_bf16 != 0 rounds weights/activations/pre-activation gradients
+// to bf16 at the same points as the tensor-core kernels; 0 is pure fp32.
+struct SimtBuffers {
+    float *x_enc;    // [B][Cx]
+    float *d_enc;    // [R][Cd]
+    float *act;      // scratch for activations: layers h1..h7, df(fc8 out), h9 -- [B][max width] each
+    float *dact;     // scratch for gradients
+    int64_t act_stride;  // floats per saved activation slab
+};
+void simt_mlp_forward(const NetGeom &g, const float *params, const float *points, const float *dirs, int64_t num_rays,
+                      int num_samples, int round_bf16, SimtBuffers &buf, float *sigma, float *rgba, cudaStream_t st);
+void simt_mlp_backward(const NetGeom &g, const float *params, float *grads, int64_t num_rays, int num_samples,
+                       int round_bf16, SimtBuffers &buf, const float *rgba, const float *d_sigma, const float *d_rgba,
+                       cudaStream_t st);
+size_t simt_act_floats_per_sample(const NetGeom &g);

@@ -1,0 +1,756 @@
+// mlp_tc.cu -- K-mlp: fused multi-layer MLP on tcgen05 tensor cores (sm_100a).
+//
+// k_chain      persistent, one CTA per SM, one 128-sample tile in flight per CTA. Warp roles:
+//                warp 0   weight-ring producer: cp.async.bulk (UBLKCP) of pre-swizzled bf16 weight
+//                         chunks [N<=128][64] from the L2-resident packed stream into a 7-stage ring;
+//                warp 1   MMA issuer: one thread issues tcgen05.mma (M=128, N<=128, K=16) with both
+//                         operands in shared memory, accumulators in TMEM (2 blocks x 128 columns);
+//                warp 2   TMEM allocator;
+//                warps 4-7 epilogue: tcgen05.ld -> +bias -> ReLU -> bf16 -> 128B-swizzled smem panel
+//                         that IS the next layer's A operand (never touches HBM in inference);
+//                         in training the panels are bulk-stored to HBM for the weight gradients.
+//              N is split in two 128-column blocks so block 0's epilogue overlaps block 1's MMAs and
+//              the next layer's first K panels (see mlp_tc_plan.cpp for the hazard argument).
+//              The positional encoding is computed in the tile prologue straight
+//              into the smem A operand of fc1 (and reused by the skip layer).
+// k_wgrad      dW^T[in x out] = sum over samples of P^T Q with both operands MN-major straight from
+//              the saved panel images; fp32 accumulators stay in TMEM across a CTA's whole sample
+//              range and are flushed once with red.global.add.f32.
+// k_pack       gathers the flat f32 [out,in] parameter blob into the bf16 chunk streams.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "mlp_tc.h"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr uint32_t kSlotBytes = NERF_PANEL_BYTES;
+constexpr uint32_t kSmemSlots = TC_NUM_SLOTS * kSlotBytes;
+constexpr uint32_t kSmemRing = TC_NUM_STAGES * TC_STAGE_BYTES;
+constexpr uint32_t kSmemBars = kSmemSlots + kSmemRing;
+constexpr uint32_t kChainSmem = kSmemBars + TC_NUM_BARS * 8 + 16;
+constexpr int kEpiThreads = 128;
+
+struct ChainArgs {
+    const MmaOp *ops;
+    const EpiJob *jobs;
+    int32_t n_ops, n_jobs;
+    const uint8_t *wpack;
+    const float *bias;
+    int64_t n_samples;
+    int32_t n_tiles, S;
+    int32_t xyz_freqs, dir_freqs;
+    const float *points;    // fwd in  [n][3]
+    const float *dirs;      // fwd in  [rays][3]
+    float *sigma;           // fwd out [n]
+    float *rgba;            // fwd out [n][4]; bwd in
+    const float *d_sigma;   // bwd in [n]
+    const float *d_rgba;    // bwd in [n][4]
+    uint8_t *save_base;     // per-tile panel area written by this launch (act or grad), or NULL
+    int32_t save_slots;
+    uint32_t *mask_base;    // [tile][mask_slots][128][8]
+    int32_t mask_slots;
+};
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t panel_chunk_addr(uint32_t slot_addr, uint32_t row, uint32_t chunk) {
+    return slot_addr + row * 128u + (((chunk ^ row) & 7u) << 4);
+}
+
+// [v, sin(2^k v), cos(2^k v)]_k for a 3-vector -> f[0 .. 3+6*freqs), zero padded to 8*kChunks.
+// sin/cos of the base angle are accurate (sincosf); octaves use the double-angle recurrence
+// (abs error <= 2^k * 1e-7, far below bf16 resolution).
+template <int kMaxF, int kChunks>
+__device__ __forceinline__ void encode_panel(uint32_t slot_addr, uint32_t row, const float v[3], int freqs) {
+    float f[8 * kChunks];
+#pragma unroll
+    for (int i = 0; i < 8 * kChunks; ++i) f[i] = 0.f;
+    f[0] = v[0]; f[1] = v[1]; f[2] = v[2];
+    float s[3], c[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) sincosf(v[d], &s[d], &c[d]);
+#pragma unroll
+    for (int k = 0; k < kMaxF; ++k) {
+        if (k < freqs) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (3 + 6 * k + d < 8 * kChunks) f[3 + 6 * k + d] = s[d];
+                if (3 + 6 * k + 3 + d < 8 * kChunks) f[3 + 6 * k + 3 + d] = c[d];
+                const float s2 = 2.f * s[d] * c[d];
+                const float c2 = fmaf(-2.f * s[d], s[d], 1.f);
+                s[d] = s2;
+                c[d] = c2;
+            }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (ch < kChunks) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16x2(f[8 * ch + 2 * e], f[8 * ch + 2 * e + 1]);
+        }
+        st_shared_v4(panel_chunk_addr(slot_addr, row, ch), w[0], w[1], w[2], w[3]);
+    }
+}
+
+__device__ __forceinline__ void write_sparse_panel(uint32_t slot_addr, uint32_t row, uint32_t w0, uint32_t w1) {
+    st_shared_v4(panel_chunk_addr(slot_addr, row, 0), w0, w1, 0u, 0u);
+#pragma unroll
+    for (int ch = 1; ch < 8; ++ch) st_shared_v4(panel_chunk_addr(slot_addr, row, ch), 0u, 0u, 0u, 0u);
+}
+
+template <bool kBwd, bool kSave>
+__global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = ptx::smem_u32(smem);
+    const uint32_t bars = sbase + kSmemBars;
+    volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kSmemBars + TC_NUM_BARS * 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023u) {
+            printf("nerf_b200: dynamic smem base not 1024-aligned\n");
+            __trap();
+        }
+        for (int s = 0; s < TC_NUM_STAGES; ++s) {
+            ptx::mbar_init(bar(TC_BAR_FULL + s), 1);
+            ptx::mbar_init(bar(TC_BAR_EMPTY + s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(bar(TC_BAR_ACC_FULL + b), 1);
+            ptx::mbar_init(bar(TC_BAR_ACC_FREE + b), 4);
+        }
+        for (int g = 0; g < 4; ++g) ptx::mbar_init(bar(TC_BAR_READY + g), 4);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<256>(ptx::smem_u32(const_cast<uint32_t *>(tmem_ptr_smem)));
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ================= weight-ring producer =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int i = 0; i < a.n_ops; ++i) {
+                    const uint32_t w_off = a.ops[i].w_off;
+                    const uint32_t bytes = (uint32_t)a.ops[i].n * 128u;
+                    ptx::mbar_wait(bar(TC_BAR_EMPTY + stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bar(TC_BAR_FULL + stage), bytes);
+                    ptx::bulk_g2s(sbase + kSmemSlots + stage * TC_STAGE_BYTES, a.wpack + w_off, bytes, bar(TC_BAR_FULL + stage));
+                    if (++stage == TC_NUM_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (single thread) =================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            // waiter-side parity per barrier id; "free"-type barriers start at 1 (first wait passes)
+            uint32_t wph = (1u << (TC_BAR_ACC_FREE + 0)) | (1u << (TC_BAR_ACC_FREE + 1));
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int i = 0; i < a.n_ops; ++i) {
+                    const MmaOp op = a.ops[i];
+                    if (op.wait0 != TC_NONE) {
+                        ptx::mbar_wait(bar(op.wait0), (wph >> op.wait0) & 1u);
+                        wph ^= 1u << op.wait0;
+                    }
+                    if (op.wait1 != TC_NONE) {
+                        ptx::mbar_wait(bar(op.wait1), (wph >> op.wait1) & 1u);
+                        wph ^= 1u << op.wait1;
+                    }
+                    ptx::mbar_wait(bar(TC_BAR_FULL + stage), phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_addr = sbase + (uint32_t)op.a_slot * kSlotBytes;
+                    const uint32_t b_addr = sbase + kSmemSlots + stage * TC_STAGE_BYTES;
+                    const uint32_t idesc = ptx::umma_idesc_bf16(128, op.n, 0, 0);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)op.acc * 128u;
+                    for (uint32_t k = 0; k < op.kcount; ++k) {
+                        const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 32u, 16, 1024);
+                        const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32u, 16, 1024);
+                        ptx::umma_ss(d_tmem, ad, bd, idesc, (k > 0 || !(op.flags & TC_OP_FIRST)) ? 1u : 0u);
+                    }
+                    ptx::umma_commit(bar(TC_BAR_EMPTY + stage));
+                    if (op.flags & TC_OP_COMMIT_ACC) ptx::umma_commit(bar(TC_BAR_ACC_FULL + op.acc));
+                    if (++stage == TC_NUM_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue warps =================
+        const uint32_t q = (uint32_t)(warp - 4);
+        const uint32_t row = q * 32u + (uint32_t)lane;
+        const bool store_thread = (threadIdx.x == 128);
+        uint32_t aph = 0;  // acc_full parities
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const int64_t gs = (int64_t)tile * NERF_TILE_M + row;
+            const bool valid = gs < a.n_samples;
+            for (int ji = 0; ji < a.n_jobs; ++ji) {
+                const EpiJob j = a.jobs[ji];
+                if (kSave) {
+                    // smem panels may still be being read by an earlier bulk store
+                    if (store_thread) ptx::bulk_wait_read<0>();
+                    ptx::named_bar_sync(1, kEpiThreads);
+                }
+                if (j.acc != TC_NONE) {
+                    ptx::mbar_wait(bar(TC_BAR_ACC_FULL + j.acc), (aph >> j.acc) & 1u);
+                    aph ^= 1u << j.acc;
+                    ptx::tc_fence_after();
+                }
+                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)(j.acc == TC_NONE ? 0 : j.acc) * 128u;
+                bool wrote_smem = false;
+
+                if (j.kind == EK_RELU || j.kind == EK_LINEAR || j.kind == EK_DMASK || j.kind == EK_DCOPY) {
+                    const int ngroups = j.ncols >> 5;
+                    uint4 mw = make_uint4(0u, 0u, 0u, 0u);  // one 32-bit relu mask word per 32-column group
+                    uint32_t *mask_ptr = nullptr;
+                    if (j.mask_slot >= 0)
+                        mask_ptr = a.mask_base + ((((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * 8 + j.mask_word0);
+                    if (kBwd && j.kind == EK_DMASK) mw = *reinterpret_cast<const uint4 *>(mask_ptr);
+                    for (int gi = 0; gi < ngroups; ++gi) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(taddr + gi * 32, r);
+                        ptx::tmem_ld_wait();
+                        if (gi == ngroups - 1) {  // accumulator block fully read: hand it back to the MMA thread
+                            ptx::tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) ptx::mbar_arrive(bar(TC_BAR_ACC_FREE + j.acc));
+                        }
+                        uint32_t w[16];
+                        if (!kBwd) {
+                            const float4 *bp = reinterpret_cast<const float4 *>(a.bias + j.bias_off + gi * 32);
+                            uint32_t signs = 0;
+#pragma unroll
+                            for (int j4 = 0; j4 < 8; ++j4) {
+                                const float4 b = __ldg(bp + j4);
+                                const float v0 = __uint_as_float(r[4 * j4 + 0]) + b.x;
+                                const float v1 = __uint_as_float(r[4 * j4 + 1]) + b.y;
+                                const float v2 = __uint_as_float(r[4 * j4 + 2]) + b.z;
+                                const float v3 = __uint_as_float(r[4 * j4 + 3]) + b.w;
+                                if (kSave && j.kind == EK_RELU) {
+                                    signs = __funnelshift_l(__float_as_uint(v0), signs, 1);
+                                    signs = __funnelshift_l(__float_as_uint(v1), signs, 1);
+                                    signs = __funnelshift_l(__float_as_uint(v2), signs, 1);
+                                    signs = __funnelshift_l(__float_as_uint(v3), signs, 1);
+                                }
+                                if (j.kind == EK_RELU) {
+                                    w[2 * j4] = ptx::pack_bf16x2_relu(v0, v1);
+                                    w[2 * j4 + 1] = ptx::pack_bf16x2_relu(v2, v3);
+                                } else {
+                                    w[2 * j4] = ptx::pack_bf16x2(v0, v1);
+                                    w[2 * j4 + 1] = ptx::pack_bf16x2(v2, v3);
+                                }
+                            }
+                            // bit (31 - col) = pre-activation sign bit clear
+                            if (gi == 0) mw.x = ~signs; else if (gi == 1) mw.y = ~signs; else if (gi == 2) mw.z = ~signs; else mw.w = ~signs;
+                        } else {
+                            const uint32_t mword = gi == 0 ? mw.x : (gi == 1 ? mw.y : (gi == 2 ? mw.z : mw.w));
+                            const uint32_t m = (j.kind == EK_DMASK) ? mword : 0xffffffffu;
+#pragma unroll
+                            for (int p = 0; p < 16; ++p) {
+                                const float v0 = (m & (0x80000000u >> (2 * p))) ? __uint_as_float(r[2 * p]) : 0.f;
+                                const float v1 = (m & (0x80000000u >> (2 * p + 1))) ? __uint_as_float(r[2 * p + 1]) : 0.f;
+                                w[p] = ptx::pack_bf16x2(v0, v1);
+                            }
+                        }
+                        const uint32_t slot_addr = sbase + (uint32_t)(j.out_slot + (gi >> 1)) * kSlotBytes;
+                        const uint32_t cb = (uint32_t)(gi & 1) * 4u;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            st_shared_v4(panel_chunk_addr(slot_addr, row, cb + c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                    }
+                    if (!kBwd && kSave && j.kind == EK_RELU && mask_ptr) *reinterpret_cast<uint4 *>(mask_ptr) = mw;
+                    wrote_smem = true;
+                } else if (j.kind == EK_SIGMA || j.kind == EK_RGBA) {
+                    uint32_t r[16];
+                    ptx::tmem_ld16(taddr, r);
+                    ptx::tmem_ld_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(bar(TC_BAR_ACC_FREE + j.acc));
+                    if (j.kind == EK_SIGMA) {
+                        if (valid) a.sigma[gs] = __uint_as_float(r[0]) + __ldg(a.bias + j.bias_off);
+                    } else if (valid) {
+                        float4 o;
+                        o.x = 1.f / (1.f + expf(-(__uint_as_float(r[0]) + __ldg(a.bias + j.bias_off + 0))));
+                        o.y = 1.f / (1.f + expf(-(__uint_as_float(r[1]) + __ldg(a.bias + j.bias_off + 1))));
+                        o.z = 1.f / (1.f + expf(-(__uint_as_float(r[2]) + __ldg(a.bias + j.bias_off + 2))));
+                        o.w = 1.f / (1.f + expf(-(__uint_as_float(r[3]) + __ldg(a.bias + j.bias_off + 3))));
+                        reinterpret_cast<float4 *>(a.rgba)[gs] = o;
+                    }
+                }
+
+                // ---- slot E producers
+                const uint32_t e_addr = sbase + TC_SLOT_E * kSlotBytes;
+                if (j.kind == EK_PROLOGUE_FWD || j.enc == ENC_X) {
+                    float v[3] = {0.f, 0.f, 0.f};
+                    if (valid) { v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2]; }
+                    encode_panel<10, 8>(e_addr, row, v, a.xyz_freqs);
+                    wrote_smem = true;
+                } else if (j.enc == ENC_D) {
+                    float v[3] = {0.f, 0.f, 0.f};
+                    if (valid) {
+                        const int64_t ray = gs / a.S;
+                        v[0] = a.dirs[3 * ray]; v[1] = a.dirs[3 * ray + 1]; v[2] = a.dirs[3 * ray + 2];
+                    }
+                    encode_panel<4, 4>(e_addr, row, v, a.dir_freqs);
+                    wrote_smem = true;
+                } else if (j.enc == ENC_DSIGMA) {
+                    const float ds = valid ? a.d_sigma[gs] : 0.f;
+                    write_sparse_panel(e_addr, row, ptx::pack_bf16x2(ds, 0.f), 0u);
+                    wrote_smem = true;
+                } else if (j.kind == EK_PROLOGUE_BWD) {
+                    float4 y = make_float4(0.f, 0.f, 0.f, 0.f), d = y;
+                    if (valid) {
+                        y = reinterpret_cast<const float4 *>(a.rgba)[gs];
+                        d = reinterpret_cast<const float4 *>(a.d_rgba)[gs];
+                    }
+                    write_sparse_panel(e_addr, row, ptx::pack_bf16x2(d.x * y.x * (1.f - y.x), d.y * y.y * (1.f - y.y)),
+                                       ptx::pack_bf16x2(d.z * y.z * (1.f - y.z), d.w * y.w * (1.f - y.w)));
+                    wrote_smem = true;
+                }
+
+                if (wrote_smem) ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to UMMA / bulk store
+                __syncwarp();
+                if (lane == 0) {
+                    if (j.ready_bar != TC_NONE) ptx::mbar_arrive(bar(j.ready_bar));
+                    if (j.enc_bar != TC_NONE) ptx::mbar_arrive(bar(j.enc_bar));
+                }
+                if (kSave && (j.save_slot >= 0 || j.enc_save_slot >= 0)) {
+                    ptx::named_bar_sync(1, kEpiThreads);
+                    if (store_thread) {
+                        uint8_t *tile_base = a.save_base + (size_t)tile * a.save_slots * kSlotBytes;
+                        if (j.save_slot >= 0) {
+                            for (int p = 0; p < (j.ncols >> 6); ++p)
+                                ptx::bulk_s2g(tile_base + (size_t)(j.save_slot + p) * kSlotBytes,
+                                              sbase + (uint32_t)(j.out_slot + p) * kSlotBytes, kSlotBytes);
+                        }
+                        if (j.enc_save_slot >= 0)
+                            ptx::bulk_s2g(tile_base + (size_t)j.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
+                        ptx::bulk_commit();
+                    }
+                }
+            }
+        }
+        if (kSave && store_thread) ptx::bulk_wait_all<0>();
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<256>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------- wgrad
+constexpr int kWgStages = 3;
+constexpr uint32_t kWgStageBytes = 65536;
+constexpr uint32_t kWgHalf = 8192;  // 64 sample rows of one panel
+constexpr uint32_t kWgBars = kWgStages * kWgStageBytes;
+constexpr uint32_t kWgSmem = kWgBars + 8 * 8 + 16 + 256 * 4;
+
+struct WgradArgs {
+    const WgradUnit *units;
+    const WgradWork *work;
+    const uint8_t *act_base;
+    const uint8_t *grad_base;
+    int32_t act_slots, grad_slots;
+    float *grads;
+};
+
+__global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = ptx::smem_u32(smem);
+    const uint32_t bars = sbase + kWgBars;  // full[3], empty[3], done
+    volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kWgBars + 64);
+    float *s_bias = reinterpret_cast<float *>(smem + kWgBars + 80);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const WgradWork wk = a.work[blockIdx.x];
+    if (wk.tile_begin >= wk.tile_end) return;  // uniform per CTA
+    const WgradUnit u = a.units[wk.unit];
+    const int n_p = u.n_p, n_q = u.n_q;
+    const int N = 64 * n_q;
+    const int mblocks = (n_p + 1) >> 1;
+    const int n_iters = (wk.tile_end - wk.tile_begin) * 2;
+
+    if (threadIdx.x == 0) {
+        if (sbase & 1023u) __trap();
+        for (int s = 0; s < kWgStages; ++s) {
+            ptx::mbar_init(bars + 8 * s, 1);
+            ptx::mbar_init(bars + 8 * (kWgStages + s), 5);  // MMA commit + 4 epilogue warps
+        }
+        ptx::mbar_init(bars + 8 * (2 * kWgStages), 1);
+        ptx::fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = 0.f;
+    if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t *>(tmem_ptr_smem)));
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t bytes = (uint32_t)(n_p + n_q) * kWgHalf;
+            for (int it = 0; it < n_iters; ++it) {
+                const int tile = wk.tile_begin + (it >> 1);
+                const uint32_t half = (uint32_t)(it & 1) * kWgHalf;
+                ptx::mbar_wait(bars + 8 * (kWgStages + stage), phase ^ 1u);
+                ptx::mbar_arrive_expect_tx(bars + 8 * stage, bytes);
+                const uint32_t dst = sbase + stage * kWgStageBytes;
+                const uint8_t *ab = a.act_base + (size_t)tile * a.act_slots * kSlotBytes + half;
+                const uint8_t *gb = a.grad_base + (size_t)tile * a.grad_slots * kSlotBytes + half;
+                for (int i = 0; i < n_p; ++i)
+                    ptx::bulk_g2s(dst + i * kWgHalf, ab + (size_t)u.p_slot[i] * kSlotBytes, kWgHalf, bars + 8 * stage);
+                for (int i = 0; i < n_q; ++i)
+                    ptx::bulk_g2s(dst + (n_p + i) * kWgHalf, gb + (size_t)u.q_slot[i] * kSlotBytes, kWgHalf, bars + 8 * stage);
+                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)N, 1, 1);
+            for (int it = 0; it < n_iters; ++it) {
+                ptx::mbar_wait(bars + 8 * stage, phase);
+                ptx::tc_fence_after();
+                const uint32_t st_addr = sbase + stage * kWgStageBytes;
+                for (int mb = 0; mb < mblocks; ++mb) {
+                    for (uint32_t k = 0; k < 4; ++k) {
+                        // 16 sample rows per K step = 2048 B; 64-element M/N blocks are kWgHalf apart
+                        const uint64_t ad = ptx::umma_desc_sw128(st_addr + (uint32_t)(2 * mb) * kWgHalf + k * 2048u, kWgHalf, 1024);
+                        const uint64_t bd = ptx::umma_desc_sw128(st_addr + (uint32_t)n_p * kWgHalf + k * 2048u, kWgHalf, 1024);
+                        ptx::umma_ss(tmem_base + (uint32_t)mb * 256u, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                ptx::umma_commit(bars + 8 * (kWgStages + stage));
+                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+            }
+            ptx::umma_commit(bars + 8 * (2 * kWgStages));
+        }
+    } else if (warp >= 4) {
+        const uint32_t q = (uint32_t)(warp - 4);
+        const int tid = threadIdx.x - 128;
+        const bool has_bias = u.b_base >= 0;
+        const int ccols = N >> 3;            // 16-byte chunk columns of Q
+        const int c8 = tid % ccols;
+        const int rg = tid / ccols;
+        const int n_rg = kEpiThreads / ccols;
+        const int rpr = 64 / n_rg;           // rows per row group per half tile
+        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t stage = 0, phase = 0;
+        for (int it = 0; it < n_iters; ++it) {
+            ptx::mbar_wait(bars + 8 * stage, phase);
+            if (has_bias) {
+                const uint32_t qaddr = sbase + stage * kWgStageBytes + (uint32_t)(n_p + (c8 >> 3)) * kWgHalf;
+                for (int rr = 0; rr < rpr; ++rr) {
+                    const uint32_t r = (uint32_t)(rg * rpr + rr);
+                    uint32_t w0, w1, w2, w3;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                 : "r"(panel_chunk_addr(qaddr, r, (uint32_t)(c8 & 7))));
+                    bsum[0] += __uint_as_float(w0 << 16); bsum[1] += __uint_as_float(w0 & 0xffff0000u);
+                    bsum[2] += __uint_as_float(w1 << 16); bsum[3] += __uint_as_float(w1 & 0xffff0000u);
+                    bsum[4] += __uint_as_float(w2 << 16); bsum[5] += __uint_as_float(w2 & 0xffff0000u);
+                    bsum[6] += __uint_as_float(w3 << 16); bsum[7] += __uint_as_float(w3 & 0xffff0000u);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bars + 8 * (kWgStages + stage));
+            if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+        }
+        if (has_bias) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_bias[c8 * 8 + e], bsum[e]);
+        }
+        ptx::named_bar_sync(1, kEpiThreads);
+        if (has_bias) {
+            for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
+        }
+        // flush the TMEM-resident dW^T block: lane = input index (contiguous in dW rows -> coalesced REDs)
+        ptx::mbar_wait(bars + 8 * (2 * kWgStages), 0);
+        ptx::tc_fence_after();
+        for (int mb = 0; mb < mblocks; ++mb) {
+            const int m = mb * 128 + (int)(q * 32) + lane;
+            for (int g = 0; g < (N >> 5); ++g) {
+                uint32_t r[32];
+                ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)g * 32u, r);
+                ptx::tmem_ld_wait();
+                if (m < u.m_valid) {
+#pragma unroll
+                    for (int jn = 0; jn < 32; ++jn) {
+                        const int n = g * 32 + jn;
+                        if (n < u.n_valid) atomicAdd(a.grads + u.w_base + (int64_t)n * u.w_row_stride + m, __uint_as_float(r[jn]));
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------- pack
+__global__ void k_pack_chunks(const PackChunk *chunks, const float *__restrict__ params, uint8_t *__restrict__ dst) {
+    const PackChunk pc = chunks[blockIdx.x];
+    for (int i = threadIdx.x; i < pc.n_rows * 8; i += blockDim.x) {
+        const int r = i >> 3, c8 = i & 7;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c8 * 8 + 2 * e + h;
+                v[h] = (r < pc.valid_rows && c < pc.valid_cols)
+                           ? params[pc.src_base + (int64_t)r * pc.row_stride + (int64_t)c * pc.col_stride]
+                           : 0.f;
+            }
+            w[e] = ptx::pack_bf16x2(v[0], v[1]);
+        }
+        *reinterpret_cast<uint4 *>(dst + pc.dst_off + (uint32_t)r * 128u + (uint32_t)(((c8 ^ r) & 7) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+__global__ void k_pack_bias(const PackBias *pb, int n, const float *__restrict__ params, float *__restrict__ dst) {
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const PackBias e = pb[b];
+        for (int i = threadIdx.x; i < e.padded; i += blockDim.x) dst[e.dst_off + i] = i < e.count ? params[e.src_base + i] : 0.f;
+    }
+}
+
+template <typename T>
+T *upload(const std::vector<T> &v) {
+    T *d = nullptr;
+    if (v.empty()) return nullptr;
+    if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    return d;
+}
+
+struct DevProgram {
+    MmaOp *ops = nullptr;
+    EpiJob *jobs = nullptr;
+    PackChunk *chunks = nullptr;
+    uint8_t *wpack = nullptr;
+    int n_ops = 0, n_jobs = 0, n_chunks = 0;
+};
+
+}  // namespace
+
+struct TcState {
+    NetGeom g;
+    TcPlan plan;
+    int num_sms = 0;
+    int64_t max_tiles = 0;
+    DevProgram fwd_train, fwd_infer, bwd;
+    PackBias *d_pbias = nullptr;
+    float *d_bias = nullptr;
+    WgradUnit *d_units = nullptr;
+    WgradWork *d_work = nullptr;
+    int64_t work_tiles = -1;
+    uint8_t *d_act = nullptr, *d_grad = nullptr;
+    uint32_t *d_mask = nullptr;
+    std::string err;
+};
+
+static bool upload_program(const TcProgram &p, DevProgram &d, bool own_weights) {
+    d.n_ops = (int)p.ops.size();
+    d.n_jobs = (int)p.jobs.size();
+    d.n_chunks = (int)p.chunks.size();
+    d.ops = upload(p.ops);
+    d.jobs = upload(p.jobs);
+    if (own_weights) {
+        d.chunks = upload(p.chunks);
+        if (cudaMalloc(&d.wpack, p.wpack_bytes) != cudaSuccess) return false;
+    }
+    return d.ops && d.jobs;
+}
+
+TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, std::string &err) {
+    TcState *s = new TcState();
+    s->g = g;
+    s->num_sms = num_sms;
+    s->max_tiles = max_tiles;
+    if (!tc_build_plan(g, s->plan, err)) { delete s; return nullptr; }
+    bool ok = upload_program(s->plan.fwd_train, s->fwd_train, true) && upload_program(s->plan.fwd_infer, s->fwd_infer, false) &&
+              upload_program(s->plan.bwd, s->bwd, true);
+    s->fwd_infer.wpack = s->fwd_train.wpack;  // identical chunk streams
+    s->d_pbias = upload(s->plan.biases);
+    s->d_units = upload(s->plan.units);
+    ok = ok && s->d_pbias && s->d_units;
+    ok = ok && cudaMalloc(&s->d_bias, sizeof(float) * s->plan.bias_floats) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->d_work, sizeof(WgradWork) * (size_t)num_sms) == cudaSuccess;
+    if (max_tiles > 0) {
+        ok = ok && cudaMalloc(&s->d_act, (size_t)max_tiles * s->plan.act_slots * kSlotBytes) == cudaSuccess;
+        ok = ok && cudaMalloc(&s->d_grad, (size_t)max_tiles * s->plan.grad_slots * kSlotBytes) == cudaSuccess;
+        ok = ok && cudaMalloc(&s->d_mask, (size_t)max_tiles * s->plan.mask_slots * NERF_TILE_M * 8 * sizeof(uint32_t)) == cudaSuccess;
+    }
+    ok = ok && cudaFuncSetAttribute(k_chain<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_chain<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_chain<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem) == cudaSuccess;
+    if (!ok) {
+        err = std::string("tc_create: allocation/attribute failure: ") + cudaGetErrorString(cudaGetLastError());
+        tc_destroy(s);
+        return nullptr;
+    }
+    return s;
+}
+
+void tc_destroy(TcState *s) {
+    if (!s) return;
+    DevProgram *ps[3] = {&s->fwd_train, &s->fwd_infer, &s->bwd};
+    for (DevProgram *p : ps) {
+        cudaFree(p->ops);
+        cudaFree(p->jobs);
+        cudaFree(p->chunks);
+    }
+    cudaFree(s->fwd_train.wpack);
+    cudaFree(s->bwd.wpack);
+    cudaFree(s->d_pbias);
+    cudaFree(s->d_bias);
+    cudaFree(s->d_units);
+    cudaFree(s->d_work);
+    cudaFree(s->d_act);
+    cudaFree(s->d_grad);
+    cudaFree(s->d_mask);
+    delete s;
+}
+
+size_t tc_bytes_per_tile(const TcState *s) {
+    return (size_t)(s->plan.act_slots + s->plan.grad_slots) * kSlotBytes + (size_t)s->plan.mask_slots * NERF_TILE_M * 32;
+}
+
+const char *tc_last_error(const TcState *s) { return s->err.c_str(); }
+
+void tc_pack_weights(TcState *s, const float *params, cudaStream_t st) {
+    k_pack_chunks<<<s->fwd_train.n_chunks, 256, 0, st>>>(s->fwd_train.chunks, params, s->fwd_train.wpack);
+    k_pack_chunks<<<s->bwd.n_chunks, 256, 0, st>>>(s->bwd.chunks, params, s->bwd.wpack);
+    k_pack_bias<<<(int)s->plan.biases.size(), 128, 0, st>>>(s->d_pbias, (int)s->plan.biases.size(), params, s->d_bias);
+}
+
+int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, int S, int train, float *sigma, float *rgba,
+               cudaStream_t st) {
+    const int64_t n_tiles = (n + NERF_TILE_M - 1) / NERF_TILE_M;
+    if (n_tiles == 0) return 0;
+    if (train && n_tiles > s->max_tiles) { s->err = "tc_forward: batch exceeds the saved-activation capacity"; return -1; }
+    const DevProgram &P = train ? s->fwd_train : s->fwd_infer;
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ops = P.ops; a.jobs = P.jobs; a.n_ops = P.n_ops; a.n_jobs = P.n_jobs;
+    a.wpack = P.wpack; a.bias = s->d_bias;
+    a.n_samples = n; a.n_tiles = (int)n_tiles; a.S = S;
+    a.xyz_freqs = s->g.xyz_freqs; a.dir_freqs = s->g.dir_freqs;
+    a.points = points; a.dirs = dirs; a.sigma = sigma; a.rgba = rgba;
+    a.save_base = train ? s->d_act : nullptr; a.save_slots = s->plan.act_slots;
+    a.mask_base = s->d_mask; a.mask_slots = s->plan.mask_slots;
+    const int grid = (int)(n_tiles < s->num_sms ? n_tiles : s->num_sms);
+    if (train) k_chain<false, true><<<grid, 256, kChainSmem, st>>>(a);
+    else k_chain<false, false><<<grid, 256, kChainSmem, st>>>(a);
+    return 0;
+}
+
+static void build_work(TcState *s, int64_t n_tiles, cudaStream_t st) {
+    if (s->work_tiles == n_tiles) return;
+    const int G = s->num_sms;
+    const int U = (int)s->plan.units.size();
+    std::vector<int> cost(U), cnt(U);
+    int total = 0;
+    for (int i = 0; i < U; ++i) { cost[i] = s->plan.units[i].n_p + s->plan.units[i].n_q; total += cost[i]; }
+    int used = 0;
+    for (int i = 0; i < U; ++i) {
+        int c = (int)((int64_t)G * cost[i] / total);
+        if (c < 1) c = 1;
+        if (c > n_tiles) c = (int)n_tiles;
+        cnt[i] = c;
+        used += c;
+    }
+    // hand out leftovers to the most loaded units (tiles per CTA), never exceeding n_tiles CTAs per unit
+    while (used < G) {
+        int best = -1;
+        double bl = 0;
+        for (int i = 0; i < U; ++i) {
+            if (cnt[i] >= n_tiles) continue;
+            const double load = (double)cost[i] / cnt[i];
+            if (load > bl) { bl = load; best = i; }
+        }
+        if (best < 0) break;
+        ++cnt[best];
+        ++used;
+    }
+    while (used > G) {  // only possible when G < U
+        int best = -1;
+        for (int i = 0; i < U; ++i) if (cnt[i] > 1 && (best < 0 || cnt[i] > cnt[best])) best = i;
+        if (best < 0) break;
+        --cnt[best];
+        --used;
+    }
+    std::vector<WgradWork> work((size_t)G, WgradWork{0, 0, 0});
+    int c = 0;
+    for (int i = 0; i < U && c < G; ++i) {
+        for (int k = 0; k < cnt[i] && c < G; ++k, ++c) {
+            work[c].unit = i;
+            work[c].tile_begin = (int)(n_tiles * k / cnt[i]);
+            work[c].tile_end = (int)(n_tiles * (k + 1) / cnt[i]);
+        }
+    }
+    cudaMemcpyAsync(s->d_work, work.data(), sizeof(WgradWork) * (size_t)G, cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);  // `work` is a host temporary
+    s->work_tiles = n_tiles;
+}
+
+int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float *d_rgba, int64_t n, float *grads,
+                cudaStream_t st, void (*between)(void *, const char *), void *user) {
+    const int64_t n_tiles = (n + NERF_TILE_M - 1) / NERF_TILE_M;
+    if (n_tiles == 0) return 0;
+    if (n_tiles > s->max_tiles) { s->err = "tc_backward: batch exceeds the saved-activation capacity"; return -1; }
+    if ((int)s->plan.units.size() > s->num_sms) { s->err = "tc_backward: fewer SMs than weight-gradient units"; return -1; }
+    build_work(s, n_tiles, st);
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ops = s->bwd.ops; a.jobs = s->bwd.jobs; a.n_ops = s->bwd.n_ops; a.n_jobs = s->bwd.n_jobs;
+    a.wpack = s->bwd.wpack; a.bias = s->d_bias;
+    a.n_samples = n; a.n_tiles = (int)n_tiles; a.S = 1;
+    a.rgba = const_cast<float *>(rgba); a.d_sigma = d_sigma; a.d_rgba = d_rgba;
+    a.save_base = s->d_grad; a.save_slots = s->plan.grad_slots;
+    a.mask_base = s->d_mask; a.mask_slots = s->plan.mask_slots;
+    const int grid = (int)(n_tiles < s->num_sms ? n_tiles : s->num_sms);
+    if (between) between(user, "mlp_dgrad");
+    k_chain<true, true><<<grid, 256, kChainSmem, st>>>(a);
+    if (between) between(user, "mlp_wgrad");
+    WgradArgs w;
+    w.units = s->d_units; w.work = s->d_work;
+    w.act_base = s->d_act; w.grad_base = s->d_grad;
+    w.act_slots = s->plan.act_slots; w.grad_slots = s->plan.grad_slots;
+    w.grads = grads;
+    k_wgrad<<<s->num_sms, 256, kWgSmem, st>>>(w);
+    if (between) between(user, nullptr);
+    return 0;
+}
+
+int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaStream_t st) {
+    if (!s || tile < 0 || tile >= s->max_tiles || slot < 0) return -1;
+    const void *src = nullptr;
+    size_t bytes = kSlotBytes;
+    if (area == 0 && slot < s->plan.act_slots) src = s->d_act + ((size_t)tile * s->plan.act_slots + slot) * kSlotBytes;
+    else if (area == 1 && slot < s->plan.grad_slots) src = s->d_grad + ((size_t)tile * s->plan.grad_slots + slot) * kSlotBytes;
+    else if (area == 2 && slot < s->plan.mask_slots) {
+        src = s->d_mask + ((size_t)tile * s->plan.mask_slots + slot) * NERF_TILE_M * 8;
+        bytes = NERF_TILE_M * 8 * sizeof(uint32_t);
+    }
+    if (!src) return -1;
+    if (cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -2;
+}

@@ -1,0 +1,134 @@
+// mlp_tc.h -- fused tcgen05/TMEM MLP: program tables + host interface.
+//
+// One persistent "chain" kernel executes a per-tile PROGRAM (built on the host from the
+// network geometry) for 128-sample tiles: a list of MMA ops (one 64-wide K panel each, fed
+// by a bulk-copy weight ring) and a list of epilogue jobs (TMEM -> registers -> bias/act ->
+// bf16 -> swizzled smem panel = next layer's A operand). The same kernel runs the forward
+// chain (fc1..fc10, src/model.rs:97-131) and the backward dgrad chain; a second kernel does
+// the weight gradients from the saved panels. See DESIGN.md section "K-mlp".
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+// smem A-operand slots (16 KB panels)
+#define TC_SLOT_E 6
+#define TC_NUM_SLOTS 7
+#define TC_NUM_STAGES 7
+#define TC_STAGE_BYTES 16384
+
+// mbarrier ids
+#define TC_BAR_FULL 0                       // +stage
+#define TC_BAR_EMPTY (TC_NUM_STAGES)        // +stage
+#define TC_BAR_ACC_FULL (2 * TC_NUM_STAGES)     // +block (2)
+#define TC_BAR_ACC_FREE (2 * TC_NUM_STAGES + 2) // +block (2)
+#define TC_BAR_READY (2 * TC_NUM_STAGES + 4)    // +group: 0 = slots 0,1; 1 = slots 2,3; 2 = slots 4,5; 3 = slot 6
+#define TC_NUM_BARS (2 * TC_NUM_STAGES + 8)
+#define TC_NONE 0xFF
+
+// MmaOp.flags
+#define TC_OP_FIRST 1u       // first K step of this accumulator block overwrites (accumulate = 0)
+#define TC_OP_COMMIT_ACC 2u  // commit to acc_full[acc] after this op
+
+struct MmaOp {
+    uint32_t w_off;   // byte offset of the weight chunk in the packed stream
+    uint16_t n;       // MMA N == chunk rows; chunk bytes = n * 128
+    uint8_t a_slot;   // smem panel slot holding the A operand
+    uint8_t acc;      // accumulator block (TMEM columns acc*128 ..)
+    uint8_t flags;
+    uint8_t wait0, wait1;  // barrier ids the MMA thread waits on before issuing (TC_NONE = none)
+    uint8_t kcount;   // K16 steps (4 = full 64-wide panel)
+};
+
+// epilogue kinds
+enum : uint8_t {
+    EK_PROLOGUE_FWD = 0,  // positions -> posenc -> slot E
+    EK_RELU = 1,          // relu(acc + bias) -> bf16 panels
+    EK_LINEAR = 2,        // acc + bias -> bf16 panels (fc8 features)
+    EK_SIGMA = 3,         // acc[0] + bias -> sigma[sample]
+    EK_RGBA = 4,          // sigmoid(acc[0..3] + bias) -> rgba[sample]
+    EK_PROLOGUE_BWD = 5,  // d_rgba * y(1-y) -> slot E (fc10 pre-activation gradient)
+    EK_DMASK = 6,         // acc * relu_mask -> bf16 panels
+    EK_DCOPY = 7,         // acc -> bf16 panels
+};
+// EpiJob.enc
+enum : uint8_t { ENC_NONE = 0, ENC_X = 1, ENC_D = 2, ENC_DSIGMA = 3 };
+
+struct EpiJob {
+    uint8_t kind;
+    uint8_t acc;        // accumulator block to wait for; TC_NONE for prologue jobs
+    uint8_t ncols;      // accumulator columns processed (multiple of 32, or 16 for SIGMA/RGBA)
+    uint8_t out_slot;   // first output smem slot (TC_NONE = none)
+    uint8_t ready_bar;  // barrier id to arrive on once the output panels are written (TC_NONE = none)
+    uint8_t enc;        // extra panel written to slot E by this job
+    uint8_t enc_bar;    // barrier id for slot E
+    uint8_t pad0;
+    int16_t save_slot;      // first per-tile global panel slot to save the output to (-1 = none)
+    int16_t enc_save_slot;  // per-tile global slot for the slot-E panel (-1 = none)
+    int16_t mask_slot;      // relu bit-mask slot: written by EK_RELU (train), read by EK_DMASK (-1 = none)
+    uint16_t mask_word0;    // first 32-bit mask word of this block within the row (0 or 4)
+    uint32_t bias_off;      // float offset into the padded bias array
+};
+
+// weight gradient unit: dW^T[in x out] block = P^T (inputs, M side) x Q (pre-activation grads, N side)
+struct WgradUnit {
+    uint8_t n_p, n_q;       // panels on the M side (1..4) and N side (1..4)
+    uint8_t pad[2];
+    int16_t p_slot[4];      // per-tile slots in the activation area
+    int16_t q_slot[4];      // per-tile slots in the gradient area
+    int32_t m_valid, n_valid;  // unpadded extents
+    int64_t w_base;         // float offset of dW[out 0][in 0] of this block in the flat gradient blob
+    int32_t w_row_stride;   // in_dim of the layer (distance between consecutive out rows)
+    int64_t b_base;         // float offset of db[out 0], or -1
+};
+struct WgradWork {          // one CTA's assignment
+    int32_t unit, tile_begin, tile_end;
+};
+
+struct PackChunk {
+    uint32_t dst_off;
+    int32_t n_rows;
+    int64_t src_base;
+    int32_t row_stride, col_stride;
+    int32_t valid_rows, valid_cols;
+};
+struct PackBias {
+    uint32_t dst_off;   // float offset in padded bias array
+    int64_t src_base;   // float offset in params
+    int32_t count, padded;
+};
+
+struct TcProgram {
+    std::vector<MmaOp> ops;
+    std::vector<EpiJob> jobs;
+    std::vector<PackChunk> chunks;
+    uint32_t wpack_bytes = 0;
+};
+
+struct TcPlan {
+    TcProgram fwd_train, fwd_infer, bwd;
+    std::vector<PackBias> biases;
+    uint32_t bias_floats = 0;
+    std::vector<WgradUnit> units;
+    int act_slots = 0, grad_slots = 0, mask_slots = 0;
+    int np = 0, np2 = 0;  // hidden panels, fc9-output panels
+};
+
+// host-only: build all tables for a geometry. Returns false (err set) if unsupported.
+bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err);
+
+struct TcState;
+TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, std::string &err);
+void tc_destroy(TcState *s);
+size_t tc_bytes_per_tile(const TcState *s);
+void tc_pack_weights(TcState *s, const float *params, cudaStream_t st);
+// points [n][3], dirs [rays][3]; n samples, S samples per ray. train -> save activations.
+int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, int S, int train, float *sigma, float *rgba,
+               cudaStream_t st);
+// dgrad chain + weight/bias gradients accumulated (+=) into grads
+int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float *d_rgba, int64_t n, float *grads,
+                cudaStream_t st, void (*between)(void *, const char *), void *user);
+const char *tc_last_error(const TcState *s);
+int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaStream_t st);

@@ -1,0 +1,363 @@
+// mlp_tc_plan.cpp -- host-side builder of the per-tile programs the fused MLP kernels run.
+//
+// Network: DensityNet fc1..fc8 and RadianceNet fc9/fc10 (src/model.rs:44-67, 85-131) with the
+// north-star options (posenc input, skip into fc6, direction into fc9). The builder emits, for
+// one 128-sample tile:
+//   * MMA ops   -- one per (GEMM, N block <=128, 64-wide K panel), in issue order, each naming the
+//                  smem slot of its A operand, the packed weight chunk it consumes from the ring,
+//                  and the mbarriers the issuing thread must wait on first;
+//   * epilogue jobs -- one per accumulator block, in order;
+//   * pack chunks   -- how to gather each weight chunk from the flat [out,in] f32 blob.
+// Hidden activations are double-buffered only for panels 0,1 (slots 0,1 <-> 2,3); panels 2,3
+// live in slots 4,5 and are rewritten in place once the GEMM that reads them has completed.
+// tests/test_tc_plan.py simulates the three roles against these tables to prove the schedule
+// is deadlock-free and hazard-free for every supported geometry.
+#include <cstdio>
+#include <cstring>
+
+#include "mlp_tc.h"
+
+namespace {
+
+struct Builder {
+    const NetGeom &g;
+    TcProgram &prog;
+    int np, np2;
+    int par = 0;                  // buffer parity currently holding hidden panels 0,1
+    bool pending[4] = {false, false, false, false};  // unconsumed "ready" event per slot group
+    std::string err;
+
+    Builder(const NetGeom &g_, TcProgram &p) : g(g_), prog(p) {
+        np = g.Wp / 64;
+        np2 = g.W2p / 64;
+    }
+    static int slot_of(int panel, int parity) { return panel < 2 ? (parity ? 2 : 0) + panel : 4 + (panel - 2); }
+    static int group_of_slot(int slot) { return slot == TC_SLOT_E ? 3 : slot / 2; }
+
+    // K-panel input descriptor for one GEMM
+    struct KIn {
+        int slot, kcount;
+        // weight source for rows (n index) r and columns c of this K panel:
+        //   element = src_base + (row0 + r) * row_stride + c * col_stride
+        int64_t src_base;
+        int row_stride, col_stride;
+        int valid_cols;
+    };
+
+    void signal(int slot, EpiJob &j, bool enc) {
+        const int grp = group_of_slot(slot);
+        if (pending[grp]) err = "schedule error: ready event not consumed before the next one";
+        pending[grp] = true;
+        if (enc) j.enc_bar = (uint8_t)(TC_BAR_READY + grp);
+        else j.ready_bar = (uint8_t)(TC_BAR_READY + grp);
+    }
+
+    // Emit the MMA ops of one accumulator block.
+    void emit_block(const std::vector<KIn> &kin, int acc, int n_mma, int row0, int valid_rows) {
+        for (size_t i = 0; i < kin.size(); ++i) {
+            const KIn &k = kin[i];
+            MmaOp op;
+            memset(&op, 0, sizeof(op));
+            op.w_off = prog.wpack_bytes;
+            op.n = (uint16_t)n_mma;
+            op.a_slot = (uint8_t)k.slot;
+            op.acc = (uint8_t)acc;
+            op.kcount = (uint8_t)k.kcount;
+            op.flags = 0;
+            op.wait0 = op.wait1 = TC_NONE;
+            if (i == 0) {
+                op.flags |= TC_OP_FIRST;
+                op.wait0 = (uint8_t)(TC_BAR_ACC_FREE + acc);
+            }
+            if (i + 1 == kin.size()) op.flags |= TC_OP_COMMIT_ACC;
+            const int grp = group_of_slot(k.slot);
+            if (pending[grp]) {
+                op.wait1 = (uint8_t)(TC_BAR_READY + grp);
+                pending[grp] = false;
+            }
+            prog.ops.push_back(op);
+            PackChunk pc;
+            pc.dst_off = prog.wpack_bytes;
+            pc.n_rows = n_mma;
+            pc.src_base = k.src_base + (int64_t)row0 * k.row_stride;
+            pc.row_stride = k.row_stride;
+            pc.col_stride = k.col_stride;
+            pc.valid_rows = valid_rows < 0 ? 0 : (valid_rows > n_mma ? n_mma : valid_rows);
+            pc.valid_cols = k.valid_cols;
+            prog.chunks.push_back(pc);
+            prog.wpack_bytes += (uint32_t)n_mma * 128u;
+        }
+    }
+
+    // Hidden-panel K inputs: panels [0, n_panels) of the current activation, weight columns
+    // start at col0 (in units of the logical matrix's K index), `valid` K entries in total.
+    void hidden_kin(std::vector<KIn> &kin, int n_panels, int64_t src_base, int row_stride, int col_stride, int col0,
+                    int valid) {
+        for (int p = 0; p < n_panels; ++p) {
+            KIn k;
+            k.slot = slot_of(p, par);
+            k.kcount = 4;
+            k.src_base = src_base + (int64_t)(col0 + 64 * p) * col_stride;
+            k.row_stride = row_stride;
+            k.col_stride = col_stride;
+            int v = valid - 64 * p;
+            k.valid_cols = v < 0 ? 0 : (v > 64 ? 64 : v);
+            kin.push_back(k);
+        }
+    }
+
+    // A GEMM whose output is a full hidden activation (n_out_panels panels), split in <=128-column
+    // blocks; block 0 goes to the other parity buffer, block 1 in place.
+    // out_row_src(r) = src row index of output row r is row0_src + r (valid n_valid rows).
+    void emit_hidden_gemm(const std::vector<KIn> &kin, int n_out_panels, int n_valid, uint8_t kind, uint32_t bias_off,
+                          int save_slot0, int mask_slot, uint8_t enc, int enc_save_slot, bool consumed) {
+        const int nblocks = n_out_panels > 2 ? 2 : 1;
+        const int newpar = par ^ 1;
+        for (int b = 0; b < nblocks; ++b) {
+            const int p0 = 2 * b;
+            const int pn = (n_out_panels - p0) > 2 ? 2 : (n_out_panels - p0);
+            emit_block(kin, b, 64 * pn, 128 * b, n_valid - 128 * b);
+        }
+        for (int b = 0; b < nblocks; ++b) {
+            const int p0 = 2 * b;
+            const int pn = (n_out_panels - p0) > 2 ? 2 : (n_out_panels - p0);
+            EpiJob j;
+            memset(&j, 0, sizeof(j));
+            j.kind = kind;
+            j.acc = (uint8_t)b;
+            j.ncols = (uint8_t)(64 * pn);
+            j.out_slot = (uint8_t)slot_of(p0, newpar);
+            j.ready_bar = TC_NONE;
+            j.enc = ENC_NONE;
+            j.enc_bar = TC_NONE;
+            j.save_slot = (int16_t)(save_slot0 < 0 ? -1 : save_slot0 + p0);
+            j.enc_save_slot = -1;
+            j.mask_slot = (int16_t)mask_slot;
+            j.mask_word0 = (uint16_t)(4 * b);
+            j.bias_off = bias_off + 128u * b;
+            if (consumed) signal(j.out_slot, j, false);
+            if (b == 0 && enc != ENC_NONE) {
+                j.enc = enc;
+                j.enc_save_slot = (int16_t)enc_save_slot;
+                signal(TC_SLOT_E, j, true);
+            }
+            prog.jobs.push_back(j);
+        }
+        par = newpar;
+    }
+
+    void emit_small_gemm(const std::vector<KIn> &kin, int acc, int valid_rows, uint8_t kind, uint32_t bias_off) {
+        emit_block(kin, acc, 16, 0, valid_rows);
+        EpiJob j;
+        memset(&j, 0, sizeof(j));
+        j.kind = kind;
+        j.acc = (uint8_t)acc;
+        j.ncols = 16;
+        j.out_slot = TC_NONE;
+        j.ready_bar = TC_NONE;
+        j.enc = ENC_NONE;
+        j.enc_bar = TC_NONE;
+        j.save_slot = j.enc_save_slot = j.mask_slot = -1;
+        j.bias_off = bias_off;
+        prog.jobs.push_back(j);
+    }
+
+    void emit_prologue(uint8_t kind, uint8_t enc, int enc_save_slot) {
+        EpiJob j;
+        memset(&j, 0, sizeof(j));
+        j.kind = kind;
+        j.acc = TC_NONE;
+        j.out_slot = TC_NONE;
+        j.ready_bar = TC_NONE;
+        j.enc = enc;
+        j.enc_bar = TC_NONE;
+        j.save_slot = -1;
+        j.mask_slot = -1;
+        j.enc_save_slot = (int16_t)enc_save_slot;
+        signal(TC_SLOT_E, j, true);
+        prog.jobs.push_back(j);
+    }
+};
+
+struct Slots {
+    int np, np2;
+    // activation area
+    int X() const { return 0; }
+    int D() const { return 1; }
+    int H(int l) const { return 2 + (l - 1) * np; }      // l = 1..7
+    int feat() const { return 2 + 7 * np; }
+    int h9() const { return 2 + 8 * np; }
+    int act_slots() const { return 2 + 8 * np + np2; }
+    // gradient area
+    int R() const { return 0; }
+    int Sg() const { return 1; }
+    int dP9() const { return 2; }
+    int dFeat() const { return 2 + np2; }
+    int dP(int l) const { return 2 + np2 + np + (7 - l) * np; }  // l = 7..1
+    int grad_slots() const { return 2 + np2 + 8 * np; }
+};
+
+}  // namespace
+
+bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
+    const int npanels = g.Wp / 64;
+    if (g.Wp % 64 || (npanels != 1 && npanels != 2 && npanels != 4) || g.W2p % 64 || g.W2p < 64 || g.W2p > 128 ||
+        g.Cx > 64 || g.Cd > 32) {
+        err = "tcgen05 MLP supports hidden <= 64, <= 128 or 129..256, xyz_freqs <= 10, dir_freqs <= 4";
+        return false;
+    }
+    if (g.skip_layer && (g.skip_layer < 1 || g.skip_layer > 6)) {
+        err = "skip_layer must be in 1..6";
+        return false;
+    }
+    const int np = g.Wp / 64, np2 = g.W2p / 64;
+    Slots sl{np, np2};
+    plan = TcPlan();
+    plan.np = np;
+    plan.np2 = np2;
+    plan.act_slots = sl.act_slots();
+    plan.grad_slots = sl.grad_slots();
+    plan.mask_slots = 8;
+
+    // ---- padded biases (forward jobs index into this array)
+    uint32_t boff = 0;
+    uint32_t bias_l[8], bias_s = 0, bias_f = 0, bias_9 = 0, bias_10 = 0;
+    for (int l = 1; l <= 7; ++l) {
+        bias_l[l] = boff;
+        plan.biases.push_back({boff, g.L[l - 1].b_off, g.W, g.Wp});
+        boff += g.Wp;
+    }
+    bias_s = boff; plan.biases.push_back({boff, g.L[7].b_off, 1, 16}); boff += 16;
+    bias_f = boff; plan.biases.push_back({boff, g.L[7].b_off + 1, g.W, g.Wp}); boff += g.Wp;
+    bias_9 = boff; plan.biases.push_back({boff, g.L[8].b_off, g.W2, g.W2p}); boff += g.W2p;
+    bias_10 = boff; plan.biases.push_back({boff, g.L[9].b_off, 4, 16}); boff += 16;
+    plan.bias_floats = boff;
+
+    // ---- forward programs (train saves panels + masks, infer does not)
+    for (int train = 0; train < 2; ++train) {
+        TcProgram &P = train ? plan.fwd_train : plan.fwd_infer;
+        Builder B(g, P);
+        B.emit_prologue(EK_PROLOGUE_FWD, ENC_X, train ? sl.X() : -1);
+        for (int l = 1; l <= 7; ++l) {
+            const LayerGeom &L = g.L[l - 1];
+            std::vector<Builder::KIn> kin;
+            const bool skip = g.skip_layer && l == g.skip_layer + 1;
+            if (l == 1 || skip) kin.push_back({TC_SLOT_E, 4, L.w_off, L.in_dim, 1, g.Cx});
+            if (l > 1) B.hidden_kin(kin, np, L.w_off, L.in_dim, 1, skip ? g.Cx : 0, g.W);
+            B.emit_hidden_gemm(kin, np, g.W, EK_RELU, bias_l[l], train ? sl.H(l) : -1, train ? (l - 1) : -1, ENC_NONE, -1,
+                               true);
+        }
+        {   // fc8 sigma row (out row 0), accumulator block 1, before the feature blocks
+            const LayerGeom &L = g.L[7];
+            std::vector<Builder::KIn> kin;
+            B.hidden_kin(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
+            B.emit_small_gemm(kin, 1, 1, EK_SIGMA, bias_s);
+        }
+        if (g.use_rgb_head) {
+            {   // fc8 features: out rows 1..W, no activation
+                const LayerGeom &L = g.L[7];
+                std::vector<Builder::KIn> kin;
+                B.hidden_kin(kin, np, L.w_off + L.in_dim, L.in_dim, 1, 0, g.W);
+                B.emit_hidden_gemm(kin, np, g.W, EK_LINEAR, bias_f, train ? sl.feat() : -1, -1, g.Cd ? ENC_D : ENC_NONE,
+                                   train ? sl.D() : -1, true);
+            }
+            {   // fc9 on [feat | dir]
+                const LayerGeom &L = g.L[8];
+                std::vector<Builder::KIn> kin;
+                if (g.Cd) kin.push_back({TC_SLOT_E, 2, L.w_off + g.W, L.in_dim, 1, g.Cd});
+                B.hidden_kin(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
+                B.emit_hidden_gemm(kin, np2, g.W2, EK_RELU, bias_9, train ? sl.h9() : -1, train ? 7 : -1, ENC_NONE, -1, true);
+            }
+            {   // fc10 + sigmoid
+                const LayerGeom &L = g.L[9];
+                std::vector<Builder::KIn> kin;
+                B.hidden_kin(kin, np2, L.w_off, L.in_dim, 1, 0, g.W2);
+                B.emit_small_gemm(kin, 1, 4, EK_RGBA, bias_10);
+            }
+        } else {
+            // sigma-only network: nothing consumes h7 after the sigma GEMM
+        }
+        if (!B.err.empty()) { err = B.err; return false; }
+        for (int i = 0; i < 4; ++i)
+            if (B.pending[i]) { err = "schedule error: unconsumed ready event at tile end (fwd)"; return false; }
+    }
+
+    // ---- backward dgrad chain
+    {
+        TcProgram &P = plan.bwd;
+        Builder B(g, P);
+        if (g.use_rgb_head) {
+            B.emit_prologue(EK_PROLOGUE_BWD, ENC_NONE, sl.R());
+            {   // dH9 = dPre10 (K=16) * W10  -> mask(h9) -> dPre9
+                const LayerGeom &L = g.L[9];
+                std::vector<Builder::KIn> kin;
+                // B chunk rows = in index (h9), cols = out index (4 valid): element = w[(c)*in_dim + r]
+                kin.push_back({TC_SLOT_E, 1, L.w_off, 1, L.in_dim, 4});
+                B.emit_hidden_gemm(kin, np2, g.W2, EK_DMASK, 0, sl.dP9(), 7, ENC_DSIGMA, sl.Sg(), true);
+            }
+            {   // dFeat = dPre9 * W9[:, 0:W]
+                const LayerGeom &L = g.L[8];
+                std::vector<Builder::KIn> kin;
+                B.hidden_kin(kin, np2, L.w_off, 1, L.in_dim, 0, g.W2);
+                B.emit_hidden_gemm(kin, np, g.W, EK_DCOPY, 0, sl.dFeat(), -1, ENC_NONE, -1, true);
+            }
+        } else {
+            B.emit_prologue(EK_PROLOGUE_BWD, ENC_DSIGMA, sl.Sg());
+        }
+        {   // dH7 = [dsigma | dFeat] * W8 -> mask(h7) -> dPre7
+            const LayerGeom &L = g.L[7];
+            std::vector<Builder::KIn> kin;
+            kin.push_back({TC_SLOT_E, 1, L.w_off, 1, L.in_dim, 1});
+            if (g.use_rgb_head) B.hidden_kin(kin, np, L.w_off + L.in_dim, 1, L.in_dim, 0, g.W);
+            B.emit_hidden_gemm(kin, np, g.W, EK_DMASK, 0, sl.dP(7), 6, ENC_NONE, -1, true);
+        }
+        for (int l = 7; l >= 2; --l) {  // dH_{l-1} = dPre_l * W_l -> mask(h_{l-1}) -> dPre_{l-1}
+            const LayerGeom &L = g.L[l - 1];
+            const bool skip = g.skip_layer && l == g.skip_layer + 1;
+            std::vector<Builder::KIn> kin;
+            B.hidden_kin(kin, np, L.w_off + (skip ? g.Cx : 0), 1, L.in_dim, 0, g.W);
+            B.emit_hidden_gemm(kin, np, g.W, EK_DMASK, 0, sl.dP(l - 1), l - 2, ENC_NONE, -1, /*consumed=*/l > 2);
+        }
+        if (!B.err.empty()) { err = B.err; return false; }
+        for (int i = 0; i < 4; ++i)
+            if (B.pending[i]) { err = "schedule error: unconsumed ready event at tile end (bwd)"; return false; }
+    }
+
+    // ---- weight-gradient units: dW^T[in x out] = P^T Q  (P = layer input panels, Q = dPre panels)
+    auto add_unit = [&](int n_p, int p0, int n_q, int q0, int m_valid, int n_valid, int64_t w_base, int row_stride,
+                        int64_t b_base) {
+        WgradUnit u;
+        memset(&u, 0, sizeof(u));
+        u.n_p = (uint8_t)n_p;
+        u.n_q = (uint8_t)n_q;
+        for (int i = 0; i < 4; ++i) { u.p_slot[i] = (int16_t)(i < n_p ? p0 + i : -1); u.q_slot[i] = (int16_t)(i < n_q ? q0 + i : -1); }
+        u.m_valid = m_valid;
+        u.n_valid = n_valid;
+        u.w_base = w_base;
+        u.w_row_stride = row_stride;
+        u.b_base = b_base;
+        plan.units.push_back(u);
+    };
+    for (int l = 1; l <= 7; ++l) {
+        const LayerGeom &L = g.L[l - 1];
+        const bool skip = g.skip_layer && l == g.skip_layer + 1;
+        if (l == 1) {
+            add_unit(1, sl.X(), np, sl.dP(1), g.Cx, g.W, L.w_off, L.in_dim, L.b_off);
+        } else {
+            if (skip) add_unit(1, sl.X(), np, sl.dP(l), g.Cx, g.W, L.w_off, L.in_dim, -1);
+            add_unit(np, sl.H(l - 1), np, sl.dP(l), g.W, g.W, L.w_off + (skip ? g.Cx : 0), L.in_dim, L.b_off);
+        }
+    }
+    {
+        const LayerGeom &L = g.L[7];
+        add_unit(np, sl.H(7), 1, sl.Sg(), g.W, 1, L.w_off, L.in_dim, L.b_off);  // sigma row
+        if (g.use_rgb_head) add_unit(np, sl.H(7), np, sl.dFeat(), g.W, g.W, L.w_off + L.in_dim, L.in_dim, L.b_off + 1);
+    }
+    if (g.use_rgb_head) {
+        const LayerGeom &L9 = g.L[8], &L10 = g.L[9];
+        add_unit(np, sl.feat(), np2, sl.dP9(), g.W, g.W2, L9.w_off, L9.in_dim, L9.b_off);
+        if (g.Cd) add_unit(1, sl.D(), np2, sl.dP9(), g.Cd, g.W2, L9.w_off + g.W, L9.in_dim, -1);
+        add_unit(np2, sl.h9(), 1, sl.R(), g.W2, 4, L10.w_off, L10.in_dim, L10.b_off);
+    }
+    return true;
+}

@@ -1,0 +1,225 @@
+// sampling.cu -- K-sample: pixel -> ray -> depth samples -> rotated world points.
+//
+// Replaces the host loops of src/ray_sampling.rs:79-178 and the gold gather of
+// src/dataset.rs:111-114. One warp per ray. Bit-exactness rules:
+// every f32 op is an explicit round-to-nearest intrinsic (no FMA contraction),
+// sqrt/div are IEEE, and cos/sin/tan never run on the device -- the per-view
+// matrices and tan(FOV/2)*HITHER come from the host.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+
+// screen_to_world (ray_sampling.rs:79-93), op for op. view=(0,0,1), left=(-1,0,0), UP=(0,1,0)
+// are the normalised constants the reference recomputes per call.
+__device__ __forceinline__ void screen_to_world(float x, float y, float width, float height, float off, float to[3]) {
+    const float two_off = mul(2.f, off);
+    const float ol = sub(off, __fdiv_rn(mul(two_off, x), width));
+    const float ou = sub(off, __fdiv_rn(mul(two_off, y), height));
+    // (view*HITHER + left*ol) + UP*ou, component-wise with the zero products kept
+    const float ax = mul(0.f, NERF_HITHER), ay = mul(0.f, NERF_HITHER), az = mul(1.f, NERF_HITHER);
+    const float bx = mul(-1.f, ol), by = mul(0.f, ol), bz = mul(0.f, ol);
+    const float cx = mul(0.f, ou), cy = mul(1.f, ou), cz = mul(0.f, ou);
+    const float sx = add(add(ax, bx), cx), sy = add(add(ay, by), cy), sz = add(add(az, bz), cz);
+    const float d = add(add(mul(sx, sx), mul(sy, sy)), mul(sz, sz));
+    const float inv = __fdiv_rn(1.f, __fsqrt_rn(d));
+    to[0] = mul(sx, inv);
+    to[1] = mul(sy, inv);
+    to[2] = mul(sz, inv);
+}
+
+__device__ __forceinline__ void rotate_yaw_pitch(const ViewPose &vp, const float v[3], float out[3]) {
+    // rotateYaw: row_mat3x4_transform_pos3 (ray_sampling.rs:20-26)
+    float y3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        y3[i] = add(add(add(mul(vp.yaw[i][0], v[0]), mul(vp.yaw[i][1], v[1])), mul(vp.yaw[i][2], v[2])), vp.yaw[i][3]);
+        // rotatePitch: col_mat3_transform (ray_sampling.rs:68)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        out[i] = add(add(mul(vp.pitch[0][i], y3[0]), mul(vp.pitch[1][i], y3[1])), mul(vp.pitch[2][i], y3[2]));
+}
+
+// Philox picks for pixel rows/cols and views (replaces Tensor::randint, dataset.rs:12,19,88).
+__global__ void k_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks, int n_views, int img_w,
+                       int img_h, uint64_t seed, int gen_pix, int gen_view) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gen_pix && i < num_rays) {
+        int y = (int)(philox_uniform(seed, NERF_STREAM_PIX_Y, (uint64_t)i) * (float)img_h);
+        int x = (int)(philox_uniform(seed, NERF_STREAM_PIX_X, (uint64_t)i) * (float)img_w);
+        pix_yx[2 * i] = min(y, img_h - 1);
+        pix_yx[2 * i + 1] = min(x, img_w - 1);
+    }
+    if (gen_view && i < n_picks) {
+        int v = (int)(philox_uniform(seed, NERF_STREAM_VIEW, (uint64_t)i) * (float)n_views);
+        view_pick[i] = min(v, n_views - 1);
+    }
+}
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kMaxS = 256;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+k_sample(SampleArgs a) {
+    __shared__ float s_t[kWarpsPerBlock][kMaxS];
+    __shared__ float s_p[kWarpsPerBlock][96];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int S = a.num_samples;
+    for (int r = blockIdx.x * kWarpsPerBlock + warp; r < a.num_rays; r += gridDim.x * kWarpsPerBlock) {
+        const int y = a.pix_yx[2 * r], x = a.pix_yx[2 * r + 1];
+        const int view = a.view_pick ? a.view_pick[r / a.rays_per_pick] : a.fixed_view;
+        const ViewPose vp = a.poses[view];
+        float to[3];
+        screen_to_world((float)x, (float)y, (float)a.img_w, (float)a.img_h, a.off, to);
+
+        // ---- depths (ray_sampling.rs:107-125)
+        float *st = s_t[warp];
+        for (int i = lane; i < S; i += 32) {
+            float t;
+            if (!a.randomize) {
+                t = mul(__fdiv_rn((float)i, (float)S), 2.0f);  // :112,:114
+            } else {
+                const float u = a.jitter ? a.jitter[(size_t)r * S + i]
+                                         : philox_uniform(a.seed, NERF_STREAM_JITTER, (uint64_t)(a.ray_index_base + r) * S + i);
+                if (a.depth_mode == 0) t = mul(u, 2.0f);                                       // :110,:114
+                else t = mul(__fdiv_rn(add((float)i, u), (float)S), 2.0f);                      // stratified
+            }
+            st[i] = t;
+        }
+        __syncwarp();
+        if (a.randomize && a.depth_mode == 0) {
+            // sort ascending by t (:125): bitonic network over the next power of two, +inf padded
+            int n = 32;
+            while (n < S) n <<= 1;
+            for (int i = S + lane; i < n; i += 32) st[i] = __int_as_float(0x7f800000);
+            __syncwarp();
+            for (int k = 2; k <= n; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = lane; i < n; i += 32) {
+                        const int l = i ^ j;
+                        if (l > i) {
+                            const float v0 = st[i], v1 = st[l];
+                            const bool up = ((i & k) == 0);
+                            if ((v0 > v1) == up) { st[i] = v1; st[l] = v0; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---- per-ray outputs
+        if (lane == 0) {
+            RayRec rec;
+            rec.to[0] = to[0]; rec.to[1] = to[1]; rec.to[2] = to[2];
+            rec.view = view;
+            a.rays[r] = rec;
+            float d[3];
+            rotate_yaw_pitch(vp, to, d);
+            a.dirs[3 * r] = d[0]; a.dirs[3 * r + 1] = d[1]; a.dirs[3 * r + 2] = d[2];
+        }
+        if (a.images && lane < 4)  // gold = imgs[n][y*W+x] (dataset.rs:111-114)
+            a.gold[4 * (size_t)r + lane] = a.images[(((size_t)view * a.img_h + y) * a.img_w + x) * 4 + lane];
+
+        // ---- points: p = FROM + to*t (:115), then yaw, pitch per point (:128-132)
+        for (int base = 0; base < S; base += 32) {
+            const int i = base + lane;
+            if (i < S) {
+                const float t = st[i];
+                a.t[(size_t)r * S + i] = t;
+                float p[3] = {add(0.f, mul(to[0], t)), add(0.f, mul(to[1], t)), add(-1.f, mul(to[2], t))};
+                float q[3];
+                rotate_yaw_pitch(vp, p, q);
+                s_p[warp][3 * lane] = q[0]; s_p[warp][3 * lane + 1] = q[1]; s_p[warp][3 * lane + 2] = q[2];
+            }
+            __syncwarp();
+            if (a.points) {
+                const int nvalid = min(32, S - base) * 3;
+                float *dst = a.points + ((size_t)r * S + base) * 3;
+                for (int k = lane; k < nvalid; k += 32) dst[k] = s_p[warp][k];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Accurate sinusoidal encoding to f32 (parity / SIMT path). out[n][3+6L]:
+// [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] per 3-vector, no pi.
+__global__ void k_encode(const float *__restrict__ x, float *__restrict__ out, int64_t n, int freqs, int repeat) {
+    const int C = 3 + 6 * freqs;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *src = x + 3 * (i / repeat);
+    float v[3] = {src[0], src[1], src[2]};
+    float *o = out + i * C;
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+    for (int k = 0; k < freqs; ++k) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float s, co;
+            sincosf(__fmul_rn(v[c], f), &s, &co);
+            o[3 + 6 * k + c] = s;
+            o[3 + 6 * k + 3 + c] = co;
+        }
+    }
+}
+
+// (c*255) as u8 saturating-truncating cast, packed 0x00RRGGBB (display.rs:37-52)
+__global__ void k_pack_0rgb(const float *__restrict__ rgba, uint32_t *__restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float v = __fmul_rn(rgba[4 * i + k], 255.f);
+        v = (v != v) ? 0.f : fminf(fmaxf(v, 0.f), 255.f);  // Rust `as u8`: NaN -> 0, saturate
+        c[k] = (uint32_t)v;
+    }
+    out[i] = (c[0] << 16) | (c[1] << 8) | c[2];
+}
+
+__global__ void k_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t n = (int64_t)(y1 - y0) * img_w;
+    if (i >= n) return;
+    pix_yx[2 * i] = y0 + (int)(i / img_w);
+    pix_yx[2 * i + 1] = (int)(i % img_w);
+}
+
+}  // namespace
+
+void launch_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks, int n_views, int img_w, int img_h,
+                 uint64_t seed, int gen_pix, int gen_view, cudaStream_t st) {
+    int n = num_rays > n_picks ? num_rays : n_picks;
+    k_pick<<<(n + 255) / 256, 256, 0, st>>>(pix_yx, view_pick, num_rays, n_picks, n_views, img_w, img_h, seed, gen_pix,
+                                            gen_view);
+}
+
+void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st) {
+    int blocks = (a.num_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int cap = num_sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_sample<<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+}
+
+void launch_encode(const float *x, float *out, int64_t n, int freqs, int repeat, cudaStream_t st) {
+    if (n <= 0) return;
+    k_encode<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, out, n, freqs, repeat);
+}
+
+void launch_pack_0rgb(const float *rgba, uint32_t *out, int64_t n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_pack_0rgb<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rgba, out, n);
+}
+
+void launch_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w, cudaStream_t st) {
+    int64_t n = (int64_t)(y1 - y0) * img_w;
+    if (n <= 0) return;
+    k_full_frame_indices<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pix_yx, y0, y1, img_w);
+}

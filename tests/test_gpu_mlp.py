@@ -1,0 +1,149 @@
+"""Fused tcgen05 MLP (and the SIMT cross-check) vs the torch oracle, through NeRF::predict /
+Trainer::step (nerf_predict_points / nerf_step). Tolerances follow the north star: MLP outputs and
+composited pixels within 1e-2 relative (bf16 MMA, fp32 accumulate)."""
+import numpy as np
+import pytest
+import torch
+
+import nerf_rs_b200 as nb
+from nerf_rs_b200 import _lib
+from oracle import model_torch as M
+from tests import gpu_util as G
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "ns256": dict(hidden=256, num_rays=8, num_samples=48),          # 384 samples = 3 tiles
+    "ns128": dict(hidden=128, num_rays=6, num_samples=64),
+    "ns64": dict(hidden=64, num_rays=4, num_samples=50),            # ragged last tile
+    "as_shipped": dict(hidden=100, xyz_freqs=0, dir_freqs=-1, skip_layer=0, use_rgb_head=0, num_rays=84, num_samples=64),
+    "ns256_big": dict(hidden=256, num_rays=1024, num_samples=64),   # config 0: 512 tiles, > 1 tile per SM
+}
+
+
+def _setup(name, impl, seed=0):
+    kw = dict(CASES[name])
+    cfg = nb.default_config(image_w=100, image_h=100, mlp_impl=impl, **kw)
+    m = nb.NeRF(cfg)
+    mcfg = G.model_cfg(cfg)
+    params_t = M.init_params(mcfg, seed)
+    m.set_weights(M.flatten_params(params_t).numpy())
+    pts, t, dirs, gold = G.make_points(cfg.num_rays, cfg.num_samples, seed + 1)
+    return m, cfg, mcfg, params_t, pts, t, dirs, gold
+
+
+def _predict(m, cfg, pts, t, dirs, train=False):
+    return m.predict(pts, t, dirs.reshape(-1) if cfg.dir_freqs >= 0 else None, train=train)
+
+
+@pytest.mark.parametrize("name", ["ns64", "ns256", "as_shipped"])
+def test_simt_fp32_matches_oracle_tightly(name):
+    m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup(name, _lib.MLP_SIMT_FP32)
+    out, sig = _predict(m, cfg, pts, t, dirs)
+    want_out, want_sig = G.oracle_predict(mcfg, params_t, pts, t, dirs, cfg.num_rays, cfg.num_samples)
+    assert np.allclose(sig, want_sig.detach().numpy(), rtol=2e-4, atol=2e-5)
+    assert np.allclose(out, want_out.detach().numpy(), rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_tcgen05_predict_matches_oracle(name):
+    m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup(name, _lib.MLP_TCGEN05)
+    out, sig = _predict(m, cfg, pts, t, dirs)
+    assert np.isfinite(out).all() and np.isfinite(sig).all()
+    # tight: oracle with bf16 rounding at the kernel's rounding points
+    e_out, e_sig = G.oracle_predict(M.replace(mcfg, emulate_bf16=True), params_t, pts, t, dirs, cfg.num_rays, cfg.num_samples)
+    assert G.rel_err(sig, e_sig.detach().numpy()) < 4e-3
+    assert G.rel_err(out, e_out.detach().numpy()) < 4e-3
+    # north-star gate: within 1e-2 relative of the fp32 reference arithmetic
+    w_out, w_sig = G.oracle_predict(mcfg, params_t, pts, t, dirs, cfg.num_rays, cfg.num_samples)
+    assert G.rel_err(out, w_out.detach().numpy()) < 1e-2
+    assert G.rel_err(sig, w_sig.detach().numpy()) < 1e-2
+
+
+@pytest.mark.parametrize("name", ["ns256", "ns128", "as_shipped", "ns256_big"])
+def test_tcgen05_matches_simt_on_device(name):
+    a = _setup(name, _lib.MLP_TCGEN05)
+    b = _setup(name, _lib.MLP_SIMT)
+    out_a, sig_a = _predict(a[0], a[1], a[4], a[5], a[6])
+    out_b, sig_b = _predict(b[0], b[1], b[4], b[5], b[6])
+    assert G.rel_err(sig_a, sig_b) < 3e-3
+    assert G.rel_err(out_a, out_b) < 3e-3
+
+
+def _layer_slices(mcfg):
+    off = 0
+    for i, o in mcfg.layer_dims():
+        yield off, off + i * o + o
+        off += i * o + o
+
+
+@pytest.mark.parametrize("name,impl", [("ns64", _lib.MLP_SIMT_FP32), ("ns256", _lib.MLP_SIMT), ("ns64", _lib.MLP_TCGEN05),
+                                       ("ns128", _lib.MLP_TCGEN05), ("ns256", _lib.MLP_TCGEN05),
+                                       ("as_shipped", _lib.MLP_TCGEN05), ("ns256_big", _lib.MLP_TCGEN05)])
+def test_step_gradients_loss_and_adam(name, impl):
+    m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup(name, impl)
+    r, s = cfg.num_rays, cfg.num_samples
+    fp32 = impl == _lib.MLP_SIMT_FP32
+    ocfg = mcfg if fp32 else M.replace(mcfg, emulate_bf16=True, emulate_bf16_grads=True)
+    tr = M.Trainer(ocfg, params_t, lr=5e-4)
+    o_out, _ = tr.predict(torch.from_numpy(pts), torch.from_numpy(t), r, s, torch.from_numpy(dirs) if mcfg.cd else None, literal=False)
+    o_loss = tr.step(o_out, torch.from_numpy(gold))
+    want_g = tr.grads_flat().numpy()
+
+    w0 = m.get_weights()
+    out, _ = _predict(m, cfg, pts, t, dirs, train=True)
+    loss = nb.Trainer(m, 5e-4).step(out, gold)
+    assert abs(loss - o_loss) <= (1e-5 if fp32 else 1e-2) * abs(o_loss) + 1e-7
+    g = m.get_grads()
+    assert np.isfinite(g).all()
+    tol = 2e-3 if fp32 else 4e-2
+    for li, (a, b) in enumerate(_layer_slices(mcfg)):
+        ref = want_g[a:b]
+        if np.abs(ref).max() == 0:      # as shipped: fc9/fc10 get no gradient
+            assert np.abs(g[a:b]).max() == 0, f"layer {li + 1} should have zero gradient"
+            continue
+        err = np.linalg.norm(g[a:b] - ref) / np.linalg.norm(ref)
+        assert err < tol, f"fc{li + 1}: relative gradient error {err:.3e}"
+    # Adam (model.rs:306-309, 322): the update applied to the kernel's own gradient is exact
+    p1, _, _ = M.adam_reference(torch.from_numpy(w0), torch.from_numpy(g), torch.zeros(g.size), torch.zeros(g.size), 1)
+    w1 = m.get_weights()
+    assert np.allclose(w1, p1.numpy(), rtol=1e-6, atol=1e-7)
+    mm, vv, step = m.get_adam_state()
+    assert step == 1 and np.allclose(mm, 0.1 * g, rtol=1e-5, atol=1e-9)
+
+
+def test_predict_asserts_like_the_reference():
+    m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup("ns64", _lib.MLP_SIMT)
+    with pytest.raises(nb.NerfError):     # model.rs:162
+        m.predict(pts[:-3], t, dirs.reshape(-1))
+    with pytest.raises(nb.NerfError):     # model.rs:163
+        m.predict(pts, t[:-1], dirs.reshape(-1))
+    with pytest.raises(nb.NerfError):     # step before predict
+        nb.Trainer(m).step(None, gold)
+    out, _ = m.predict(pts, t, dirs.reshape(-1))
+    with pytest.raises(nb.NerfError):     # model.rs:316
+        nb.Trainer(m).step(out, gold[:-4])
+
+
+def test_loss_curve_1k_steps_within_2_percent():
+    """North-star gate: loss curves over 1k steps stay within 2% of the reference arithmetic."""
+    kw = dict(hidden=64, num_rays=32, num_samples=32)
+    cfg = nb.default_config(image_w=100, image_h=100, mlp_impl=_lib.MLP_TCGEN05, **kw)
+    m = nb.NeRF(cfg)
+    mcfg = G.model_cfg(cfg)
+    params_t = M.init_params(mcfg, 3)
+    m.set_weights(M.flatten_params(params_t).numpy())
+    pts, t, dirs, gold = G.make_points(cfg.num_rays, cfg.num_samples, 9)
+    tr = M.Trainer(mcfg, params_t, lr=5e-4)
+    trn = nb.Trainer(m, 5e-4)
+    tp, tt, td, tg = torch.from_numpy(pts), torch.from_numpy(t), torch.from_numpy(dirs), torch.from_numpy(gold)
+    ref, got = [], []
+    for it in range(1000):
+        o, _ = tr.predict(tp, tt, cfg.num_rays, cfg.num_samples, td, literal=False)
+        ref.append(tr.step(o, tg))
+        out, _ = m.predict(pts, t, dirs.reshape(-1), train=True, want_sigma=False)
+        got.append(trn.step(out, gold))
+    ref, got = np.array(ref), np.array(got)
+    assert got[-1] < got[0] * 0.8                      # it actually trains
+    assert np.abs(got - ref).max() <= 0.02 * ref.max()
+    assert np.abs(got[-100:].mean() - ref[-100:].mean()) <= 0.02 * ref[-100:].mean()
