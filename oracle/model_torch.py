@@ -255,7 +255,9 @@ class Trainer:
         return float(loss.detach())
 
     def grads_flat(self):
-        return torch.cat([torch.cat([w.grad.reshape(-1), b.grad.reshape(-1)]) for w, b in self.params])
+        def g(p):  # as shipped fc9/fc10 receive no gradient: report zeros
+            return (p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+        return torch.cat([torch.cat([g(w), g(b)]) for w, b in self.params])
 
     def params_flat(self):
         return flatten_params([(w.detach(), b.detach()) for w, b in self.params])

