@@ -33,6 +33,10 @@ int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3,
  * area 2 = relu bit masks (slot = mask slot, out = 128*8 uint32). */
 int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slot, void *out);
 
+/* Run one chain program (0 forward-train, 1 forward-inference, 2 backward dgrad) on the resident
+ * batch with clock64 tracing of CTA 0. out: [3 roles (MMA issuer, epilogue warp 0, producer)][2048][2]. */
+int nerf_debug_trace(nerf_ctx *ctx, int32_t program, uint64_t *out);
+
 #ifdef __cplusplus
 }
 #endif

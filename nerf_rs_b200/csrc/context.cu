@@ -1023,6 +1023,20 @@ int nerf_debug_read_panel(nerf_ctx *c, int32_t area, int32_t tile, int32_t slot,
     return NERF_OK;
 }
 
+int nerf_debug_trace(nerf_ctx *c, int32_t program, uint64_t *out) {
+    if (!c || !out) return NERF_ERR_INVALID_ARG;
+    if (!c->tc) return fail(c, NERF_ERR_STATE, "debug_trace: not a tcgen05 context");
+    if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "debug_trace: no batch");
+    CU(c, cudaSetDevice(c->device));
+    int rc = ensure_packed(c);
+    if (rc) return rc;
+    const int nr = c->chunk < c->R ? c->chunk : c->R;
+    if (tc_debug_trace(c->tc, c->d_points, c->d_dirs, (int64_t)nr * c->S, c->S, program, c->d_rgba, c->d_dsigma, c->d_drgba,
+                       c->d_sigma, c->d_rgba, (unsigned long long *)out, c->stream))
+        return fail(c, NERF_ERR_CUDA, "debug_trace failed");
+    return check_launch(c, "debug_trace");
+}
+
 int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3, float *off) {
     ViewPose vp;
     make_pose(yaw, pitch, vp);

@@ -1,0 +1,148 @@
+// nerf_b200.hpp -- C++ host-side mirror of the reference's call surface over the C ABI.
+//
+// The reference host is Rust (src/main.rs:57-72); the Rust toolchain is absent from the build
+// image, so the compiled-language host layer above the C ABI is this header (the Rust binding of
+// the same surface ships as source in ffi/rust/). Names and argument meaning follow the reference:
+//   nerf::NeRF::predict            <- NeRF::predict            src/model.rs:152-209
+//   nerf::compositing              <- compositing              src/model.rs:234-249
+//   nerf::Trainer::step            <- Trainer::step            src/model.rs:311-325
+//   nerf::get_multiview_batch      <- dataset::get_multiview_batch  src/dataset.rs:63-139
+// Where the reference panics (assert_eq!/unwrap) these throw nerf::Error; nothing throws across
+// the C ABI itself.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../../include/nerf_b200.h"
+
+namespace nerf {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string &m) : std::runtime_error(m), status(s) {}
+};
+
+inline void check(nerf_ctx *c, int status) {
+    if (status != NERF_OK)
+        throw Error(status, std::string(nerf_strerror(status)) + (c ? std::string(": ") + nerf_last_error(c) : std::string()));
+}
+
+inline std::vector<std::pair<float, float>> get_view_angles(int num_views) {  // image_loading.rs:67-80
+    std::vector<float> buf(4 * (size_t)num_views * (num_views + 1));
+    check(nullptr, nerf_view_angles_grid(num_views, buf.data(), (int32_t)buf.size()));
+    std::vector<std::pair<float, float>> out(buf.size() / 2);
+    for (size_t i = 0; i < out.size(); ++i) out[i] = {buf[2 * i], buf[2 * i + 1]};
+    return out;
+}
+
+class NeRF {
+   public:
+    explicit NeRF(const nerf_config &cfg, int device = 0) : cfg_(cfg) { check(nullptr, nerf_create(&cfg_, device, &ctx_)); }
+    NeRF() : NeRF(default_config()) {}   // NeRF::new() (model.rs:140)
+    ~NeRF() { nerf_destroy(ctx_); }
+    NeRF(const NeRF &) = delete;
+    NeRF &operator=(const NeRF &) = delete;
+
+    static nerf_config default_config() {
+        nerf_config c;
+        check(nullptr, nerf_default_config(&c));
+        return c;
+    }
+    static nerf_config as_shipped_config() {
+        nerf_config c;
+        check(nullptr, nerf_config_as_shipped(&c));
+        return c;
+    }
+
+    // (pixels [R*4], densities [R*S]) -- query_points [B*3], distances [B] (model.rs:152-156)
+    std::pair<std::vector<float>, std::vector<float>> predict(const std::vector<float> &query_points,
+                                                              const std::vector<float> &distances,
+                                                              const std::vector<float> *dirs = nullptr, bool train = true) {
+        std::vector<float> out((size_t)cfg_.num_rays * 4), sig((size_t)cfg_.num_rays * cfg_.num_samples);
+        check(ctx_, nerf_predict_points(ctx_, query_points.data(), (int64_t)query_points.size(), distances.data(),
+                                        (int64_t)distances.size(), dirs ? dirs->data() : nullptr, train ? 1 : 0, out.data(), sig.data()));
+        return {std::move(out), std::move(sig)};
+    }
+    std::vector<float> predict_resident(bool train = true) {
+        std::vector<float> out((size_t)cfg_.num_rays * 4);
+        check(ctx_, nerf_predict(ctx_, train ? 1 : 0, out.data(), nullptr));
+        return out;
+    }
+    void save_weights(std::vector<float> &flat) {  // NeRF::save surface (model.rs:211-213)
+        flat.resize((size_t)nerf_num_params(ctx_));
+        check(ctx_, nerf_get_weights(ctx_, flat.data(), (int64_t)flat.size()));
+    }
+    void load_weights(const std::vector<float> &flat) {  // NeRF::load surface (model.rs:215-217)
+        check(ctx_, nerf_set_weights(ctx_, flat.data(), (int64_t)flat.size()));
+    }
+    void set_images(const std::vector<std::vector<std::array<float, 4>>> &imgs) {
+        std::vector<float> flat;
+        for (auto &im : imgs)
+            for (auto &px : im) flat.insert(flat.end(), px.begin(), px.end());
+        check(ctx_, nerf_set_images(ctx_, flat.data(), (int32_t)imgs.size()));
+        n_views_ = (int)imgs.size();
+    }
+    void set_view_angles(const std::vector<std::pair<float, float>> &va) {
+        std::vector<float> flat;
+        for (auto &p : va) { flat.push_back(p.first); flat.push_back(p.second); }
+        check(ctx_, nerf_set_view_angles(ctx_, flat.data(), (int32_t)va.size()));
+    }
+    nerf_ctx *ctx() { return ctx_; }
+    const nerf_config &config() const { return cfg_; }
+    int n_views() const { return n_views_; }
+
+   private:
+    nerf_config cfg_;
+    nerf_ctx *ctx_ = nullptr;
+    int n_views_ = 0;
+};
+
+// compositing(&densities [R,S], colors [R,S,4], distances [R,S]) -> [R,4]  (model.rs:234)
+inline std::vector<float> compositing(NeRF &m, const std::vector<float> &densities, const std::vector<float> *colors,
+                                      const std::vector<float> &distances, int num_rays, int num_samples) {
+    std::vector<float> out((size_t)num_rays * 4);
+    check(m.ctx(), nerf_compositing(m.ctx(), densities.data(), colors ? colors->data() : nullptr, distances.data(), num_rays,
+                                    num_samples, out.data()));
+    return out;
+}
+
+class Trainer {  // Trainer::new(&vs, lr) / step (model.rs:301-325)
+   public:
+    explicit Trainer(NeRF &m) : m_(m) {}
+    float step(const std::vector<float> &predictions, const std::vector<float> &gold, size_t /*iter*/ = 0) {
+        if (predictions.size() != (size_t)m_.config().num_rays * 4) throw Error(NERF_ERR_INVALID_ARG, "predictions must be [NUM_RAYS, LABELS]");
+        float loss = 0.f;
+        check(m_.ctx(), nerf_step(m_.ctx(), gold.data(), (int64_t)gold.size(), &loss));
+        return loss;
+    }
+
+   private:
+    NeRF &m_;
+};
+
+// get_multiview_batch(&imgs, &view_angles) -> (indices [R][2], query_points [R*S*3], distances [R*S], gold [R*4])
+// Images / angles must already be resident (set_images / set_view_angles).
+template <class Rng>
+inline std::tuple<std::vector<std::array<int64_t, 2>>, std::vector<float>, std::vector<float>, std::vector<float>>
+get_multiview_batch(NeRF &m, Rng &rng) {
+    const nerf_config &c = m.config();
+    const int R = c.num_rays, S = c.num_samples, V = m.n_views();
+    if (V < 1 || R % V != 0) throw Error(NERF_ERR_INVALID_ARG, "Can't divide rays evenly among views (dataset.rs:73-81)");
+    std::vector<int64_t> idx(2 * (size_t)R), vi((size_t)V);
+    std::uniform_int_distribution<int64_t> dy(0, c.image_h - 1), dx(0, c.image_w - 1), dv(0, V - 1);
+    for (int i = 0; i < R; ++i) { idx[2 * i] = dy(rng); idx[2 * i + 1] = dx(rng); }
+    for (int i = 0; i < V; ++i) vi[i] = dv(rng);
+    std::vector<float> pts((size_t)R * S * 3), t((size_t)R * S), gold((size_t)R * 4);
+    check(m.ctx(), nerf_get_batch(m.ctx(), idx.data(), vi.data(), V, nullptr, 1, (uint64_t)rng(), pts.data(), t.data(), gold.data(),
+                                  nullptr, nullptr));
+    std::vector<std::array<int64_t, 2>> indices((size_t)R);
+    for (int i = 0; i < R; ++i) indices[i] = {idx[2 * i], idx[2 * i + 1]};
+    return {std::move(indices), std::move(pts), std::move(t), std::move(gold)};
+}
+
+}  // namespace nerf

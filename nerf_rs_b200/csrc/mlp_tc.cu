@@ -31,9 +31,12 @@ namespace {
 constexpr uint32_t kSlotBytes = NERF_PANEL_BYTES;
 constexpr uint32_t kSmemSlots = TC_NUM_SLOTS * kSlotBytes;
 constexpr uint32_t kSmemRing = TC_NUM_STAGES * TC_STAGE_BYTES;
-constexpr uint32_t kSmemBars = kSmemSlots + kSmemRing;
+constexpr uint32_t kSmemTables = kSmemSlots + kSmemRing;      // bias | ops | jobs copies
+constexpr uint32_t kTableBytes = 12288;
+constexpr uint32_t kSmemBars = kSmemTables + kTableBytes;
 constexpr uint32_t kChainSmem = kSmemBars + TC_NUM_BARS * 8 + 16;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;
+constexpr int kChainThreads = 32 * (4 + kEpiWarps);
 
 struct ChainArgs {
     const MmaOp *ops;
@@ -41,6 +44,7 @@ struct ChainArgs {
     int32_t n_ops, n_jobs;
     const uint8_t *wpack;
     const float *bias;
+    int32_t bias_floats;
     int64_t n_samples;
     int32_t n_tiles, S;
     int32_t xyz_freqs, dir_freqs;
@@ -54,7 +58,16 @@ struct ChainArgs {
     int32_t save_slots;
     uint32_t *mask_base;    // [tile][mask_slots][128][8]
     int32_t mask_slots;
+    unsigned long long *trace;  // debug: [3 roles][kTraceEvents][2] clock64 stamps of CTA 0, or NULL
 };
+constexpr int kTraceEvents = 2048;
+
+__device__ __forceinline__ void trace_event(const ChainArgs &a, int role, int idx, unsigned long long t0, unsigned long long t1) {
+    if (a.trace && blockIdx.x == 0 && idx < kTraceEvents) {
+        a.trace[((size_t)role * kTraceEvents + idx) * 2] = t0;
+        a.trace[((size_t)role * kTraceEvents + idx) * 2 + 1] = t1;
+    }
+}
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -63,14 +76,14 @@ __device__ __forceinline__ uint32_t panel_chunk_addr(uint32_t slot_addr, uint32_
     return slot_addr + row * 128u + (((chunk ^ row) & 7u) << 4);
 }
 
-// [v, sin(2^k v), cos(2^k v)]_k for a 3-vector -> f[0 .. 3+6*freqs), zero padded to 8*kChunks.
-// sin/cos of the base angle are accurate (sincosf); octaves use the double-angle recurrence
-// (abs error <= 2^k * 1e-7, far below bf16 resolution).
-template <int kMaxF, int kChunks>
+// [v, sin(2^k v), cos(2^k v)]_k for a 3-vector -> f[0 .. 3+6*freqs), zero padded; this warp packs and
+// stores only the 16-byte chunks [kCh0, kCh1) of the row. sin/cos of the base angle are accurate
+// (sincosf); octaves use the double-angle recurrence (abs error <= 2^k * 1e-7, far below bf16 resolution).
+template <int kMaxF, int kCh0, int kCh1>
 __device__ __forceinline__ void encode_panel(uint32_t slot_addr, uint32_t row, const float v[3], int freqs) {
-    float f[8 * kChunks];
+    float f[64];
 #pragma unroll
-    for (int i = 0; i < 8 * kChunks; ++i) f[i] = 0.f;
+    for (int i = 0; i < 64; ++i) f[i] = 0.f;
     f[0] = v[0]; f[1] = v[1]; f[2] = v[2];
     float s[3], c[3];
 #pragma unroll
@@ -80,8 +93,8 @@ __device__ __forceinline__ void encode_panel(uint32_t slot_addr, uint32_t row, c
         if (k < freqs) {
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                if (3 + 6 * k + d < 8 * kChunks) f[3 + 6 * k + d] = s[d];
-                if (3 + 6 * k + 3 + d < 8 * kChunks) f[3 + 6 * k + 3 + d] = c[d];
+                f[3 + 6 * k + d] = s[d];
+                f[3 + 6 * k + 3 + d] = c[d];
                 const float s2 = 2.f * s[d] * c[d];
                 const float c2 = fmaf(-2.f * s[d], s[d], 1.f);
                 s[d] = s2;
@@ -90,30 +103,121 @@ __device__ __forceinline__ void encode_panel(uint32_t slot_addr, uint32_t row, c
         }
     }
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        if (ch < kChunks) {
+    for (int ch = kCh0; ch < kCh1; ++ch) {
+        uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16x2(f[8 * ch + 2 * e], f[8 * ch + 2 * e + 1]);
-        }
+        for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16x2(f[8 * ch + 2 * e], f[8 * ch + 2 * e + 1]);
         st_shared_v4(panel_chunk_addr(slot_addr, row, ch), w[0], w[1], w[2], w[3]);
     }
 }
 
-__device__ __forceinline__ void write_sparse_panel(uint32_t slot_addr, uint32_t row, uint32_t w0, uint32_t w1) {
-    st_shared_v4(panel_chunk_addr(slot_addr, row, 0), w0, w1, 0u, 0u);
+// panel whose only non-zero entries are the first four bf16 of each row; half h writes chunks 4h..4h+3
+__device__ __forceinline__ void write_sparse_panel(uint32_t slot_addr, uint32_t row, uint32_t h, uint32_t w0, uint32_t w1) {
 #pragma unroll
-    for (int ch = 1; ch < 8; ++ch) st_shared_v4(panel_chunk_addr(slot_addr, row, ch), 0u, 0u, 0u, 0u);
+    for (int ch = 0; ch < 4; ++ch) {
+        const bool first = (h == 0 && ch == 0);
+        st_shared_v4(panel_chunk_addr(slot_addr, row, 4 * h + ch), first ? w0 : 0u, first ? w1 : 0u, 0u, 0u);
+    }
+}
+
+
+// One 32-column group of a hidden-layer epilogue: accumulator registers -> (bias, activation | relu mask)
+// -> 16 packed bf16x2 words. kKind selects the arithmetic at compile time.
+template <bool kSave, uint8_t kKind>
+__device__ __forceinline__ void epi_group(const uint32_t (&r)[32], const float *bias_g, uint32_t &mask, uint32_t (&w)[16]) {
+    if (kKind == EK_RELU || kKind == EK_LINEAR) {
+        const float4 *bp = reinterpret_cast<const float4 *>(bias_g);
+        uint32_t signs = 0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = bp[j4];
+            const float v0 = __uint_as_float(r[4 * j4 + 0]) + b.x;
+            const float v1 = __uint_as_float(r[4 * j4 + 1]) + b.y;
+            const float v2 = __uint_as_float(r[4 * j4 + 2]) + b.z;
+            const float v3 = __uint_as_float(r[4 * j4 + 3]) + b.w;
+            if (kSave && kKind == EK_RELU) {
+                signs = __funnelshift_l(__float_as_uint(v0), signs, 1);
+                signs = __funnelshift_l(__float_as_uint(v1), signs, 1);
+                signs = __funnelshift_l(__float_as_uint(v2), signs, 1);
+                signs = __funnelshift_l(__float_as_uint(v3), signs, 1);
+            }
+            if (kKind == EK_RELU) {
+                w[2 * j4] = ptx::pack_bf16x2_relu(v0, v1);
+                w[2 * j4 + 1] = ptx::pack_bf16x2_relu(v2, v3);
+            } else {
+                w[2 * j4] = ptx::pack_bf16x2(v0, v1);
+                w[2 * j4 + 1] = ptx::pack_bf16x2(v2, v3);
+            }
+        }
+        mask = ~signs;  // bit (31 - col) = pre-activation sign bit clear
+    } else {
+        const uint32_t m = (kKind == EK_DMASK) ? mask : 0xffffffffu;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            const float v0 = (m & (0x80000000u >> (2 * p))) ? __uint_as_float(r[2 * p]) : 0.f;
+            const float v1 = (m & (0x80000000u >> (2 * p + 1))) ? __uint_as_float(r[2 * p + 1]) : 0.f;
+            w[p] = ptx::pack_bf16x2(v0, v1);
+        }
+    }
+}
+
+__device__ __forceinline__ void store_group(uint32_t slot_addr, uint32_t row, uint32_t cb, const uint32_t (&w)[16]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+        st_shared_v4(panel_chunk_addr(slot_addr, row, cb + c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+
+// Hidden-layer epilogue job for one warp: `gcount` (1 or 2) groups starting at group g0 of the block.
+template <bool kSave, uint8_t kKind>
+__device__ __forceinline__ void epi_hidden(const EpiJob &j, uint32_t taddr, uint32_t sbase, const float *s_bias, uint32_t *mask_ptr,
+                                           uint32_t row, int g0, int gcount, uint32_t acc_free_bar, int lane) {
+    uint32_t r0[32], r1[32];
+    uint32_t m0 = 0, m1 = 0;
+    if (kKind == EK_DMASK) {
+        m0 = mask_ptr[0];
+        if (gcount > 1) m1 = mask_ptr[1];
+    }
+    ptx::tmem_ld32(taddr + g0 * 32, r0);
+    if (gcount > 1) ptx::tmem_ld32(taddr + (g0 + 1) * 32, r1);
+    ptx::tmem_ld_wait();
+    // this warp's share of the accumulator is in registers: after the GEMM's last job, hand the set back
+    if (acc_free_bar) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_free_bar);
+    }
+    uint32_t w[16];
+    epi_group<kSave, kKind>(r0, s_bias + j.bias_off + g0 * 32, m0, w);
+    store_group(sbase + (uint32_t)(j.out_slot + (g0 >> 1)) * kSlotBytes, row, (uint32_t)(g0 & 1) * 4u, w);
+    if (gcount > 1) {
+        epi_group<kSave, kKind>(r1, s_bias + j.bias_off + (g0 + 1) * 32, m1, w);
+        store_group(sbase + (uint32_t)(j.out_slot + ((g0 + 1) >> 1)) * kSlotBytes, row, (uint32_t)((g0 + 1) & 1) * 4u, w);
+    }
+    if (kSave && kKind == EK_RELU && mask_ptr) {
+        mask_ptr[0] = m0;
+        if (gcount > 1) mask_ptr[1] = m1;
+    }
 }
 
 template <bool kBwd, bool kSave>
-__global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
+__global__ void __launch_bounds__(kChainThreads, 1) k_chain(const ChainArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t bars = sbase + kSmemBars;
     volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kSmemBars + TC_NUM_BARS * 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
+
+    // tables live in shared memory: with ~220 KB of the SM's 228 KB carved out as smem the L1 is tiny,
+    // so per-op / per-job / bias reads from global would each pay an L2 round trip on the critical path
+    float *s_bias = reinterpret_cast<float *>(smem + kSmemTables);
+    MmaOp *s_ops = reinterpret_cast<MmaOp *>(smem + kSmemTables + ((a.bias_floats * 4 + 15) & ~15));
+    EpiJob *s_jobs = reinterpret_cast<EpiJob *>(reinterpret_cast<uint8_t *>(s_ops) + ((a.n_ops * (int)sizeof(MmaOp) + 15) & ~15));
+    for (int i = threadIdx.x; i < a.bias_floats; i += blockDim.x) s_bias[i] = a.bias[i];
+    for (int i = threadIdx.x; i < a.n_ops * (int)(sizeof(MmaOp) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_ops)[i] = reinterpret_cast<const uint32_t *>(a.ops)[i];
+    for (int i = threadIdx.x; i < a.n_jobs * (int)(sizeof(EpiJob) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t *>(s_jobs)[i] = reinterpret_cast<const uint32_t *>(a.jobs)[i];
 
     if (threadIdx.x == 0) {
         if (sbase & 1023u) {
@@ -126,12 +230,12 @@ __global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(bar(TC_BAR_ACC_FULL + b), 1);
-            ptx::mbar_init(bar(TC_BAR_ACC_FREE + b), 4);
+            ptx::mbar_init(bar(TC_BAR_ACC_FREE + b), kEpiWarps);
         }
-        for (int g = 0; g < 4; ++g) ptx::mbar_init(bar(TC_BAR_READY + g), 4);
+        for (int g = 0; g < 4; ++g) ptx::mbar_init(bar(TC_BAR_READY + g), kEpiWarps);
         ptx::fence_mbar_init();
     }
-    if (warp == 2) ptx::tmem_alloc<256>(ptx::smem_u32(const_cast<uint32_t *>(tmem_ptr_smem)));
+    if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t *>(tmem_ptr_smem)));
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -139,218 +243,220 @@ __global__ void __launch_bounds__(256, 1) k_chain(const ChainArgs a) {
 
     if (warp == 0) {
         // ================= weight-ring producer =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                for (int i = 0; i < a.n_ops; ++i) {
-                    const uint32_t w_off = a.ops[i].w_off;
-                    const uint32_t bytes = (uint32_t)a.ops[i].n * 128u;
-                    ptx::mbar_wait(bar(TC_BAR_EMPTY + stage), phase ^ 1u);
+        // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers);
+        // one elected lane issues the bulk copy.
+        uint32_t stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int i = 0; i < a.n_ops; ++i) {
+                const uint32_t w_off = s_ops[i].w_off;
+                const uint32_t bytes = (uint32_t)s_ops[i].n * 128u;
+                const unsigned long long tp0 = a.trace ? clock64() : 0;
+                ptx::mbar_wait(bar(TC_BAR_EMPTY + stage), phase ^ 1u);
+                if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(bar(TC_BAR_FULL + stage), bytes);
                     ptx::bulk_g2s(sbase + kSmemSlots + stage * TC_STAGE_BYTES, a.wpack + w_off, bytes, bar(TC_BAR_FULL + stage));
-                    if (++stage == TC_NUM_STAGES) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (a.trace && lane == 0) trace_event(a, 2, (tile - blockIdx.x) / gridDim.x * a.n_ops + i, tp0, clock64());
+                if (++stage == TC_NUM_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer (single thread) =================
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            // waiter-side parity per barrier id; "free"-type barriers start at 1 (first wait passes)
-            uint32_t wph = (1u << (TC_BAR_ACC_FREE + 0)) | (1u << (TC_BAR_ACC_FREE + 1));
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                for (int i = 0; i < a.n_ops; ++i) {
-                    const MmaOp op = a.ops[i];
-                    if (op.wait0 != TC_NONE) {
-                        ptx::mbar_wait(bar(op.wait0), (wph >> op.wait0) & 1u);
-                        wph ^= 1u << op.wait0;
-                    }
-                    if (op.wait1 != TC_NONE) {
-                        ptx::mbar_wait(bar(op.wait1), (wph >> op.wait1) & 1u);
-                        wph ^= 1u << op.wait1;
-                    }
-                    ptx::mbar_wait(bar(TC_BAR_FULL + stage), phase);
-                    ptx::tc_fence_after();
-                    const uint32_t a_addr = sbase + (uint32_t)op.a_slot * kSlotBytes;
-                    const uint32_t b_addr = sbase + kSmemSlots + stage * TC_STAGE_BYTES;
-                    const uint32_t idesc = ptx::umma_idesc_bf16(128, op.n, 0, 0);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)op.acc * 128u;
-                    for (uint32_t k = 0; k < op.kcount; ++k) {
-                        const uint64_t ad = ptx::umma_desc_sw128(a_addr + k * 32u, 16, 1024);
-                        const uint64_t bd = ptx::umma_desc_sw128(b_addr + k * 32u, 16, 1024);
-                        ptx::umma_ss(d_tmem, ad, bd, idesc, (k > 0 || !(op.flags & TC_OP_FIRST)) ? 1u : 0u);
+        // ================= MMA issuer =================
+        // Warp-uniform loop; tcgen05.mma / tcgen05.commit are issued by one elected lane. (A plain
+        // `if (lane == 0)` makes ptxas wrap every UTCHMMA in an elect/branch convergence loop and
+        // rebuild its uniform-register operands, ~100 cycles per instruction.)
+        uint32_t stage = 0, phase = 0;
+        // waiter-side parity per barrier id; "free"-type barriers start at 1 (first wait passes)
+        uint32_t wph = (1u << (TC_BAR_ACC_FREE + 0)) | (1u << (TC_BAR_ACC_FREE + 1));
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int i = 0; i < a.n_ops; ++i) {
+                const MmaOp op = s_ops[i];
+                const unsigned long long tm0 = a.trace ? clock64() : 0;
+                if (op.wait0 != TC_NONE) {
+                    ptx::mbar_wait(bar(op.wait0), (wph >> op.wait0) & 1u);
+                    wph ^= 1u << op.wait0;
+                }
+                if (op.wait1 != TC_NONE) {
+                    ptx::mbar_wait(bar(op.wait1), (wph >> op.wait1) & 1u);
+                    wph ^= 1u << op.wait1;
+                }
+                const unsigned long long tm1 = a.trace ? clock64() : 0;
+                ptx::mbar_wait(bar(TC_BAR_FULL + stage), phase);
+                ptx::tc_fence_after();
+                const unsigned long long tm2 = a.trace ? clock64() : 0;
+                const uint32_t a_addr = sbase + (uint32_t)op.a_slot * kSlotBytes;
+                const uint32_t b_addr = sbase + kSmemSlots + stage * TC_STAGE_BYTES;
+                const uint32_t idesc = ptx::umma_idesc_bf16(128, op.n, 0, 0);
+                const uint32_t d_tmem = tmem_base + (uint32_t)op.acc * 256u;
+                const uint64_t ad0 = ptx::umma_desc_sw128(a_addr, 16, 1024);
+                const uint64_t bd0 = ptx::umma_desc_sw128(b_addr, 16, 1024);
+                const uint32_t acc_first = (op.flags & TC_OP_FIRST) ? 0u : 1u;
+                if (ptx::elect_one()) {
+                    // +32 B per K16 step == +2 in the descriptor's address field
+                    ptx::umma_ss(d_tmem, ad0, bd0, idesc, acc_first);
+                    if (op.kcount > 1) ptx::umma_ss(d_tmem, ad0 + 2u, bd0 + 2u, idesc, 1u);
+                    if (op.kcount > 2) {
+                        ptx::umma_ss(d_tmem, ad0 + 4u, bd0 + 4u, idesc, 1u);
+                        ptx::umma_ss(d_tmem, ad0 + 6u, bd0 + 6u, idesc, 1u);
                     }
                     ptx::umma_commit(bar(TC_BAR_EMPTY + stage));
                     if (op.flags & TC_OP_COMMIT_ACC) ptx::umma_commit(bar(TC_BAR_ACC_FULL + op.acc));
-                    if (++stage == TC_NUM_STAGES) { stage = 0; phase ^= 1u; }
                 }
+                __syncwarp();
+                if (a.trace && lane == 0) {
+                    const int ev = ((tile - blockIdx.x) / gridDim.x * a.n_ops + i) * 2;
+                    trace_event(a, 0, ev, tm0, tm1);
+                    trace_event(a, 0, ev + 1, tm2, clock64());
+                }
+                if (++stage == TC_NUM_STAGES) { stage = 0; phase ^= 1u; }
             }
         }
     } else if (warp >= 4) {
         // ================= epilogue warps =================
-        const uint32_t q = (uint32_t)(warp - 4);
+        // warp (q, h): TMEM lane quarter q (rows 32q..32q+31), column half h of each accumulator block
+        const uint32_t we = (uint32_t)(warp - 4);
+        const uint32_t q = we & 3u, h = we >> 2;
         const uint32_t row = q * 32u + (uint32_t)lane;
-        const bool store_thread = (threadIdx.x == 128);
+        const bool store_lane = (h == 0 && lane == 0);   // issues this row quarter's bulk stores
         uint32_t aph = 0;  // acc_full parities
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
             const int64_t gs = (int64_t)tile * NERF_TILE_M + row;
             const bool valid = gs < a.n_samples;
             for (int ji = 0; ji < a.n_jobs; ++ji) {
-                const EpiJob j = a.jobs[ji];
+                const EpiJob j = s_jobs[ji];
+                const bool writes_e = (j.acc == TC_NONE) || (j.enc != ENC_NONE);
                 if (kSave) {
-                    // smem panels may still be being read by an earlier bulk store
-                    if (store_thread) ptx::bulk_wait_read<0>();
-                    ptx::named_bar_sync(1, kEpiThreads);
+                    // a panel may still be the source of an earlier bulk store of this row quarter: hidden
+                    // panels rotate with period >= 2 store groups, slot E is rewritten back to back
+                    if (store_lane) {
+                        if (writes_e) ptx::bulk_wait_read<0>();
+                        else ptx::bulk_wait_read<1>();
+                    }
+                    ptx::named_bar_sync(2 + q, 64);
                 }
-                if (j.acc != TC_NONE) {
+                const unsigned long long te0 = a.trace ? clock64() : 0;
+                if (j.flags & TC_JOB_WAIT_ACC) {
                     ptx::mbar_wait(bar(TC_BAR_ACC_FULL + j.acc), (aph >> j.acc) & 1u);
                     aph ^= 1u << j.acc;
                     ptx::tc_fence_after();
                 }
-                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)(j.acc == TC_NONE ? 0 : j.acc) * 128u;
+                const unsigned long long te1 = a.trace ? clock64() : 0;
+                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)j.acc_col;
                 bool wrote_smem = false;
 
                 if (j.kind == EK_RELU || j.kind == EK_LINEAR || j.kind == EK_DMASK || j.kind == EK_DCOPY) {
-                    const int ngroups = j.ncols >> 5;
-                    uint4 mw = make_uint4(0u, 0u, 0u, 0u);  // one 32-bit relu mask word per 32-column group
+                    const int gcount = j.ncols >> 6;            // 32-column groups per warp (1 or 2)
+                    const int g0 = (int)h * gcount;
                     uint32_t *mask_ptr = nullptr;
                     if (j.mask_slot >= 0)
-                        mask_ptr = a.mask_base + ((((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * 8 + j.mask_word0);
-                    if (kBwd && j.kind == EK_DMASK) mw = *reinterpret_cast<const uint4 *>(mask_ptr);
-                    for (int gi = 0; gi < ngroups; ++gi) {
-                        uint32_t r[32];
-                        ptx::tmem_ld32(taddr + gi * 32, r);
-                        ptx::tmem_ld_wait();
-                        if (gi == ngroups - 1) {  // accumulator block fully read: hand it back to the MMA thread
-                            ptx::tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) ptx::mbar_arrive(bar(TC_BAR_ACC_FREE + j.acc));
-                        }
-                        uint32_t w[16];
-                        if (!kBwd) {
-                            const float4 *bp = reinterpret_cast<const float4 *>(a.bias + j.bias_off + gi * 32);
-                            uint32_t signs = 0;
-#pragma unroll
-                            for (int j4 = 0; j4 < 8; ++j4) {
-                                const float4 b = __ldg(bp + j4);
-                                const float v0 = __uint_as_float(r[4 * j4 + 0]) + b.x;
-                                const float v1 = __uint_as_float(r[4 * j4 + 1]) + b.y;
-                                const float v2 = __uint_as_float(r[4 * j4 + 2]) + b.z;
-                                const float v3 = __uint_as_float(r[4 * j4 + 3]) + b.w;
-                                if (kSave && j.kind == EK_RELU) {
-                                    signs = __funnelshift_l(__float_as_uint(v0), signs, 1);
-                                    signs = __funnelshift_l(__float_as_uint(v1), signs, 1);
-                                    signs = __funnelshift_l(__float_as_uint(v2), signs, 1);
-                                    signs = __funnelshift_l(__float_as_uint(v3), signs, 1);
-                                }
-                                if (j.kind == EK_RELU) {
-                                    w[2 * j4] = ptx::pack_bf16x2_relu(v0, v1);
-                                    w[2 * j4 + 1] = ptx::pack_bf16x2_relu(v2, v3);
-                                } else {
-                                    w[2 * j4] = ptx::pack_bf16x2(v0, v1);
-                                    w[2 * j4 + 1] = ptx::pack_bf16x2(v2, v3);
-                                }
-                            }
-                            // bit (31 - col) = pre-activation sign bit clear
-                            if (gi == 0) mw.x = ~signs; else if (gi == 1) mw.y = ~signs; else if (gi == 2) mw.z = ~signs; else mw.w = ~signs;
-                        } else {
-                            const uint32_t mword = gi == 0 ? mw.x : (gi == 1 ? mw.y : (gi == 2 ? mw.z : mw.w));
-                            const uint32_t m = (j.kind == EK_DMASK) ? mword : 0xffffffffu;
-#pragma unroll
-                            for (int p = 0; p < 16; ++p) {
-                                const float v0 = (m & (0x80000000u >> (2 * p))) ? __uint_as_float(r[2 * p]) : 0.f;
-                                const float v1 = (m & (0x80000000u >> (2 * p + 1))) ? __uint_as_float(r[2 * p + 1]) : 0.f;
-                                w[p] = ptx::pack_bf16x2(v0, v1);
-                            }
-                        }
-                        const uint32_t slot_addr = sbase + (uint32_t)(j.out_slot + (gi >> 1)) * kSlotBytes;
-                        const uint32_t cb = (uint32_t)(gi & 1) * 4u;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            st_shared_v4(panel_chunk_addr(slot_addr, row, cb + c), w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+                        mask_ptr = a.mask_base + ((((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * 8 + j.mask_word0 + g0);
+                    const uint32_t fb = (j.flags & TC_JOB_RELEASE_ACC) ? bar(TC_BAR_ACC_FREE + j.acc) : 0u;
+                    if (!kBwd) {
+                        if (j.kind == EK_RELU) epi_hidden<kSave, EK_RELU>(j, taddr, sbase, s_bias, mask_ptr, row, g0, gcount, fb, lane);
+                        else epi_hidden<kSave, EK_LINEAR>(j, taddr, sbase, s_bias, mask_ptr, row, g0, gcount, fb, lane);
+                    } else {
+                        if (j.kind == EK_DMASK) epi_hidden<kSave, EK_DMASK>(j, taddr, sbase, s_bias, mask_ptr, row, g0, gcount, fb, lane);
+                        else epi_hidden<kSave, EK_DCOPY>(j, taddr, sbase, s_bias, mask_ptr, row, g0, gcount, fb, lane);
                     }
-                    if (!kBwd && kSave && j.kind == EK_RELU && mask_ptr) *reinterpret_cast<uint4 *>(mask_ptr) = mw;
                     wrote_smem = true;
                 } else if (j.kind == EK_SIGMA || j.kind == EK_RGBA) {
-                    uint32_t r[16];
-                    ptx::tmem_ld16(taddr, r);
-                    ptx::tmem_ld_wait();
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(bar(TC_BAR_ACC_FREE + j.acc));
-                    if (j.kind == EK_SIGMA) {
-                        if (valid) a.sigma[gs] = __uint_as_float(r[0]) + __ldg(a.bias + j.bias_off);
-                    } else if (valid) {
-                        float4 o;
-                        o.x = 1.f / (1.f + expf(-(__uint_as_float(r[0]) + __ldg(a.bias + j.bias_off + 0))));
-                        o.y = 1.f / (1.f + expf(-(__uint_as_float(r[1]) + __ldg(a.bias + j.bias_off + 1))));
-                        o.z = 1.f / (1.f + expf(-(__uint_as_float(r[2]) + __ldg(a.bias + j.bias_off + 2))));
-                        o.w = 1.f / (1.f + expf(-(__uint_as_float(r[3]) + __ldg(a.bias + j.bias_off + 3))));
-                        reinterpret_cast<float4 *>(a.rgba)[gs] = o;
+                    if (h == 0) {
+                        uint32_t r[16];
+                        ptx::tmem_ld16(taddr, r);
+                        ptx::tmem_ld_wait();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) ptx::mbar_arrive(bar(TC_BAR_ACC_FREE + j.acc));
+                        if (j.kind == EK_SIGMA) {
+                            if (valid) a.sigma[gs] = __uint_as_float(r[0]) + s_bias[j.bias_off];
+                        } else if (valid) {
+                            float4 o;
+                            o.x = 1.f / (1.f + expf(-(__uint_as_float(r[0]) + s_bias[j.bias_off + 0])));
+                            o.y = 1.f / (1.f + expf(-(__uint_as_float(r[1]) + s_bias[j.bias_off + 1])));
+                            o.z = 1.f / (1.f + expf(-(__uint_as_float(r[2]) + s_bias[j.bias_off + 2])));
+                            o.w = 1.f / (1.f + expf(-(__uint_as_float(r[3]) + s_bias[j.bias_off + 3])));
+                            reinterpret_cast<float4 *>(a.rgba)[gs] = o;
+                        }
+                    } else if (lane == 0) {
+                        ptx::mbar_arrive(bar(TC_BAR_ACC_FREE + j.acc));  // this half reads nothing
                     }
                 }
 
-                // ---- slot E producers
+                // ---- slot E producers (each column half writes four of the eight 16-byte chunks per row)
                 const uint32_t e_addr = sbase + TC_SLOT_E * kSlotBytes;
                 if (j.kind == EK_PROLOGUE_FWD || j.enc == ENC_X) {
                     float v[3] = {0.f, 0.f, 0.f};
                     if (valid) { v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2]; }
-                    encode_panel<10, 8>(e_addr, row, v, a.xyz_freqs);
+                    if (h == 0) encode_panel<10, 0, 4>(e_addr, row, v, a.xyz_freqs);
+                    else encode_panel<10, 4, 8>(e_addr, row, v, a.xyz_freqs);
                     wrote_smem = true;
                 } else if (j.enc == ENC_D) {
-                    float v[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        const int64_t ray = gs / a.S;
-                        v[0] = a.dirs[3 * ray]; v[1] = a.dirs[3 * ray + 1]; v[2] = a.dirs[3 * ray + 2];
+                    if (h == 0) {
+                        float v[3] = {0.f, 0.f, 0.f};
+                        if (valid) {
+                            const int64_t ray = gs / a.S;
+                            v[0] = a.dirs[3 * ray]; v[1] = a.dirs[3 * ray + 1]; v[2] = a.dirs[3 * ray + 2];
+                        }
+                        encode_panel<4, 0, 4>(e_addr, row, v, a.dir_freqs);
+                    } else {
+                        write_sparse_panel(e_addr, row, 1, 0u, 0u);
                     }
-                    encode_panel<4, 4>(e_addr, row, v, a.dir_freqs);
                     wrote_smem = true;
                 } else if (j.enc == ENC_DSIGMA) {
                     const float ds = valid ? a.d_sigma[gs] : 0.f;
-                    write_sparse_panel(e_addr, row, ptx::pack_bf16x2(ds, 0.f), 0u);
+                    write_sparse_panel(e_addr, row, h, ptx::pack_bf16x2(ds, 0.f), 0u);
                     wrote_smem = true;
                 } else if (j.kind == EK_PROLOGUE_BWD) {
                     float4 y = make_float4(0.f, 0.f, 0.f, 0.f), d = y;
-                    if (valid) {
+                    if (valid && h == 0) {
                         y = reinterpret_cast<const float4 *>(a.rgba)[gs];
                         d = reinterpret_cast<const float4 *>(a.d_rgba)[gs];
                     }
-                    write_sparse_panel(e_addr, row, ptx::pack_bf16x2(d.x * y.x * (1.f - y.x), d.y * y.y * (1.f - y.y)),
+                    write_sparse_panel(e_addr, row, h, ptx::pack_bf16x2(d.x * y.x * (1.f - y.x), d.y * y.y * (1.f - y.y)),
                                        ptx::pack_bf16x2(d.z * y.z * (1.f - y.z), d.w * y.w * (1.f - y.w)));
                     wrote_smem = true;
                 }
 
+                const unsigned long long te2 = a.trace ? clock64() : 0;
                 if (wrote_smem) ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to UMMA / bulk store
                 __syncwarp();
                 if (lane == 0) {
                     if (j.ready_bar != TC_NONE) ptx::mbar_arrive(bar(j.ready_bar));
                     if (j.enc_bar != TC_NONE) ptx::mbar_arrive(bar(j.enc_bar));
                 }
+                if (a.trace && we == 0 && lane == 0) {
+                    const int ev = ((tile - blockIdx.x) / gridDim.x * a.n_jobs + ji) * 2;
+                    trace_event(a, 1, ev, te0, te1);
+                    trace_event(a, 1, ev + 1, te2, clock64());
+                }
                 if (kSave && (j.save_slot >= 0 || j.enc_save_slot >= 0)) {
-                    ptx::named_bar_sync(1, kEpiThreads);
-                    if (store_thread) {
-                        uint8_t *tile_base = a.save_base + (size_t)tile * a.save_slots * kSlotBytes;
+                    ptx::named_bar_sync(2 + q, 64);   // both column halves of this row quarter are written
+                    if (store_lane) {
+                        // rows 32q..32q+31 of a panel image are one contiguous 4 KB block
+                        uint8_t *tile_base = a.save_base + (size_t)tile * a.save_slots * kSlotBytes + q * 4096u;
                         if (j.save_slot >= 0) {
                             for (int p = 0; p < (j.ncols >> 6); ++p)
                                 ptx::bulk_s2g(tile_base + (size_t)(j.save_slot + p) * kSlotBytes,
-                                              sbase + (uint32_t)(j.out_slot + p) * kSlotBytes, kSlotBytes);
+                                              sbase + (uint32_t)(j.out_slot + p) * kSlotBytes + q * 4096u, 4096u);
                         }
                         if (j.enc_save_slot >= 0)
-                            ptx::bulk_s2g(tile_base + (size_t)j.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
+                            ptx::bulk_s2g(tile_base + (size_t)j.enc_save_slot * kSlotBytes, e_addr + q * 4096u, 4096u);
                         ptx::bulk_commit();
                     }
                 }
             }
         }
-        if (kSave && store_thread) ptx::bulk_wait_all<0>();
+        if (kSave && store_lane) ptx::bulk_wait_all<0>();
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 2) ptx::tmem_dealloc<256>(tmem_base);
+    if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------- wgrad
+constexpr int kEpiThreads = 128;
 constexpr int kWgStages = 3;
 constexpr uint32_t kWgStageBytes = 65536;
 constexpr uint32_t kWgHalf = 8192;  // 64 sample rows of one panel
@@ -584,6 +690,10 @@ TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, std::string
     s->num_sms = num_sms;
     s->max_tiles = max_tiles;
     if (!tc_build_plan(g, s->plan, err)) { delete s; return nullptr; }
+    for (const TcProgram *p : {&s->plan.fwd_train, &s->plan.fwd_infer, &s->plan.bwd}) {
+        const size_t need = ((s->plan.bias_floats * 4 + 15) & ~15u) + ((p->ops.size() * sizeof(MmaOp) + 15) & ~15u) + p->jobs.size() * sizeof(EpiJob);
+        if (need > kTableBytes) { err = "tc_create: program tables exceed the shared-memory table area"; delete s; return nullptr; }
+    }
     bool ok = upload_program(s->plan.fwd_train, s->fwd_train, true) && upload_program(s->plan.fwd_infer, s->fwd_infer, false) &&
               upload_program(s->plan.bwd, s->bwd, true);
     s->fwd_infer.wpack = s->fwd_train.wpack;  // identical chunk streams
@@ -650,15 +760,15 @@ int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, in
     ChainArgs a;
     memset(&a, 0, sizeof(a));
     a.ops = P.ops; a.jobs = P.jobs; a.n_ops = P.n_ops; a.n_jobs = P.n_jobs;
-    a.wpack = P.wpack; a.bias = s->d_bias;
+    a.wpack = P.wpack; a.bias = s->d_bias; a.bias_floats = (int)s->plan.bias_floats;
     a.n_samples = n; a.n_tiles = (int)n_tiles; a.S = S;
     a.xyz_freqs = s->g.xyz_freqs; a.dir_freqs = s->g.dir_freqs;
     a.points = points; a.dirs = dirs; a.sigma = sigma; a.rgba = rgba;
     a.save_base = train ? s->d_act : nullptr; a.save_slots = s->plan.act_slots;
     a.mask_base = s->d_mask; a.mask_slots = s->plan.mask_slots;
     const int grid = (int)(n_tiles < s->num_sms ? n_tiles : s->num_sms);
-    if (train) k_chain<false, true><<<grid, 256, kChainSmem, st>>>(a);
-    else k_chain<false, false><<<grid, 256, kChainSmem, st>>>(a);
+    if (train) k_chain<false, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
+    else k_chain<false, false><<<grid, kChainThreads, kChainSmem, st>>>(a);
     return 0;
 }
 
@@ -721,14 +831,14 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
     ChainArgs a;
     memset(&a, 0, sizeof(a));
     a.ops = s->bwd.ops; a.jobs = s->bwd.jobs; a.n_ops = s->bwd.n_ops; a.n_jobs = s->bwd.n_jobs;
-    a.wpack = s->bwd.wpack; a.bias = s->d_bias;
+    a.wpack = s->bwd.wpack; a.bias = s->d_bias; a.bias_floats = (int)s->plan.bias_floats;
     a.n_samples = n; a.n_tiles = (int)n_tiles; a.S = 1;
     a.rgba = const_cast<float *>(rgba); a.d_sigma = d_sigma; a.d_rgba = d_rgba;
     a.save_base = s->d_grad; a.save_slots = s->plan.grad_slots;
     a.mask_base = s->d_mask; a.mask_slots = s->plan.mask_slots;
     const int grid = (int)(n_tiles < s->num_sms ? n_tiles : s->num_sms);
     if (between) between(user, "mlp_dgrad");
-    k_chain<true, true><<<grid, 256, kChainSmem, st>>>(a);
+    k_chain<true, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
     if (between) between(user, "mlp_wgrad");
     WgradArgs w;
     w.units = s->d_units; w.work = s->d_work;
@@ -753,4 +863,36 @@ int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaS
     if (!src) return -1;
     if (cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
     return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -2;
+}
+
+int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n, int S, int program, const float *rgba,
+                   const float *d_sigma, const float *d_rgba, float *sigma_out, float *rgba_out, unsigned long long *host_out,
+                   cudaStream_t st) {
+    const int64_t n_tiles = (n + NERF_TILE_M - 1) / NERF_TILE_M;
+    if (n_tiles == 0 || (program != 1 && n_tiles > s->max_tiles)) return -1;
+    unsigned long long *d_trace = nullptr;
+    const size_t bytes = sizeof(unsigned long long) * 3 * kTraceEvents * 2;
+    if (cudaMalloc(&d_trace, bytes) != cudaSuccess) return -2;
+    cudaMemsetAsync(d_trace, 0, bytes, st);
+    const DevProgram &P = program == 0 ? s->fwd_train : (program == 1 ? s->fwd_infer : s->bwd);
+    ChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ops = P.ops; a.jobs = P.jobs; a.n_ops = P.n_ops; a.n_jobs = P.n_jobs;
+    a.wpack = P.wpack; a.bias = s->d_bias; a.bias_floats = (int)s->plan.bias_floats;
+    a.n_samples = n; a.n_tiles = (int)n_tiles; a.S = S;
+    a.xyz_freqs = s->g.xyz_freqs; a.dir_freqs = s->g.dir_freqs;
+    a.points = points; a.dirs = dirs; a.sigma = sigma_out; a.rgba = program == 2 ? const_cast<float *>(rgba) : rgba_out;
+    a.d_sigma = d_sigma; a.d_rgba = d_rgba;
+    a.save_base = program == 0 ? s->d_act : (program == 2 ? s->d_grad : nullptr);
+    a.save_slots = program == 2 ? s->plan.grad_slots : s->plan.act_slots;
+    a.mask_base = s->d_mask; a.mask_slots = s->plan.mask_slots;
+    a.trace = d_trace;
+    const int grid = (int)(n_tiles < s->num_sms ? n_tiles : s->num_sms);
+    if (program == 0) k_chain<false, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
+    else if (program == 1) k_chain<false, false><<<grid, kChainThreads, kChainSmem, st>>>(a);
+    else k_chain<true, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
+    cudaMemcpyAsync(host_out, d_trace, bytes, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_trace);
+    return e == cudaSuccess ? 0 : -2;
 }

@@ -13,18 +13,18 @@
 
 #include "common.cuh"
 
-// smem A-operand slots (16 KB panels)
-#define TC_SLOT_E 6
-#define TC_NUM_SLOTS 7
-#define TC_NUM_STAGES 7
-#define TC_STAGE_BYTES 16384
+// smem A-operand slots (16 KB panels): hidden panels 0..3 (rewritten in place), E = encoded inputs
+#define TC_SLOT_E 4
+#define TC_NUM_SLOTS 5
+#define TC_NUM_STAGES 4
+#define TC_STAGE_BYTES 32768   // one weight chunk [N <= 256][64 bf16]
 
 // mbarrier ids
 #define TC_BAR_FULL 0                       // +stage
 #define TC_BAR_EMPTY (TC_NUM_STAGES)        // +stage
-#define TC_BAR_ACC_FULL (2 * TC_NUM_STAGES)     // +block (2)
-#define TC_BAR_ACC_FREE (2 * TC_NUM_STAGES + 2) // +block (2)
-#define TC_BAR_READY (2 * TC_NUM_STAGES + 4)    // +group: 0 = slots 0,1; 1 = slots 2,3; 2 = slots 4,5; 3 = slot 6
+#define TC_BAR_ACC_FULL (2 * TC_NUM_STAGES)     // +accumulator set (2)
+#define TC_BAR_ACC_FREE (2 * TC_NUM_STAGES + 2) // +accumulator set (2)
+#define TC_BAR_READY (2 * TC_NUM_STAGES + 4)    // +group: 0 = slots 0,1; 1 = slots 2,3; 2 = slot E
 #define TC_NUM_BARS (2 * TC_NUM_STAGES + 8)
 #define TC_NONE 0xFF
 
@@ -34,9 +34,9 @@
 
 struct MmaOp {
     uint32_t w_off;   // byte offset of the weight chunk in the packed stream
-    uint16_t n;       // MMA N == chunk rows; chunk bytes = n * 128
+    uint16_t n;       // MMA N == chunk rows (<= 256); chunk bytes = n * 128
     uint8_t a_slot;   // smem panel slot holding the A operand
-    uint8_t acc;      // accumulator block (TMEM columns acc*128 ..)
+    uint8_t acc;      // accumulator set (TMEM columns acc*256 ..); GEMMs alternate sets
     uint8_t flags;
     uint8_t wait0, wait1;  // barrier ids the MMA thread waits on before issuing (TC_NONE = none)
     uint8_t kcount;   // K16 steps (4 = full 64-wide panel)
@@ -56,20 +56,25 @@ enum : uint8_t {
 // EpiJob.enc
 enum : uint8_t { ENC_NONE = 0, ENC_X = 1, ENC_D = 2, ENC_DSIGMA = 3 };
 
+// EpiJob.flags
+#define TC_JOB_WAIT_ACC 1u     // first job of a GEMM: wait for acc_full[acc]
+#define TC_JOB_RELEASE_ACC 2u  // last job of a GEMM: arrive on acc_free[acc] once its TMEM reads are done
+
 struct EpiJob {
     uint8_t kind;
-    uint8_t acc;        // accumulator block to wait for; TC_NONE for prologue jobs
-    uint8_t ncols;      // accumulator columns processed (multiple of 32, or 16 for SIGMA/RGBA)
+    uint8_t acc;        // accumulator set; TC_NONE for prologue jobs
+    uint8_t ncols;      // accumulator columns processed (multiple of 64, or 16 for SIGMA/RGBA)
     uint8_t out_slot;   // first output smem slot (TC_NONE = none)
     uint8_t ready_bar;  // barrier id to arrive on once the output panels are written (TC_NONE = none)
     uint8_t enc;        // extra panel written to slot E by this job
     uint8_t enc_bar;    // barrier id for slot E
-    uint8_t pad0;
+    uint8_t flags;
     int16_t save_slot;      // first per-tile global panel slot to save the output to (-1 = none)
     int16_t enc_save_slot;  // per-tile global slot for the slot-E panel (-1 = none)
     int16_t mask_slot;      // relu bit-mask slot: written by EK_RELU (train), read by EK_DMASK (-1 = none)
     uint16_t mask_word0;    // first 32-bit mask word of this block within the row (0 or 4)
-    uint32_t bias_off;      // float offset into the padded bias array
+    uint16_t bias_off;      // float offset into the padded bias array
+    uint16_t acc_col;       // first TMEM column of this job's block (set*256 + 128*block)
 };
 
 // weight gradient unit: dW^T[in x out] block = P^T (inputs, M side) x Q (pre-activation grads, N side)
@@ -132,3 +137,8 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
                 cudaStream_t st, void (*between)(void *, const char *), void *user);
 const char *tc_last_error(const TcState *s);
 int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaStream_t st);
+// debug: run one chain program (0 fwd-train, 1 fwd-infer, 2 bwd) with clock64 tracing of CTA 0.
+// host_out: [3 roles (mma, epilogue warp 0, producer)][2048 events][2] uint64.
+int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n, int S, int program, const float *rgba,
+                   const float *d_sigma, const float *d_rgba, float *sigma_out, float *rgba_out, unsigned long long *host_out,
+                   cudaStream_t st);

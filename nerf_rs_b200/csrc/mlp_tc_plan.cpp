@@ -8,8 +8,9 @@
 //                  and the mbarriers the issuing thread must wait on first;
 //   * epilogue jobs -- one per accumulator block, in order;
 //   * pack chunks   -- how to gather each weight chunk from the flat [out,in] f32 blob.
-// Hidden activations are double-buffered only for panels 0,1 (slots 0,1 <-> 2,3); panels 2,3
-// live in slots 4,5 and are rewritten in place once the GEMM that reads them has completed.
+// Every GEMM issues full-width MMAs (N = layer width, <= 256) into one of two TMEM accumulator sets;
+// consecutive GEMMs alternate sets, so a layer's epilogue (reading set s, rewriting the hidden
+// panels in place) overlaps the next layer's MMAs (writing set s^1) panel pair by panel pair.
 // tests/test_tc_plan.py simulates the three roles against these tables to prove the schedule
 // is deadlock-free and hazard-free for every supported geometry.
 #include <cstdio>
@@ -23,22 +24,21 @@ struct Builder {
     const NetGeom &g;
     TcProgram &prog;
     int np, np2;
-    int par = 0;                  // buffer parity currently holding hidden panels 0,1
-    bool pending[4] = {false, false, false, false};  // unconsumed "ready" event per slot group
+    int set = 0;                  // accumulator set the next GEMM uses
+    bool pending[3] = {false, false, false};  // unconsumed "ready" event per slot group
     std::string err;
 
     Builder(const NetGeom &g_, TcProgram &p) : g(g_), prog(p) {
         np = g.Wp / 64;
         np2 = g.W2p / 64;
     }
-    static int slot_of(int panel, int parity) { return panel < 2 ? (parity ? 2 : 0) + panel : 4 + (panel - 2); }
-    static int group_of_slot(int slot) { return slot == TC_SLOT_E ? 3 : slot / 2; }
+    static int group_of_slot(int slot) { return slot == TC_SLOT_E ? 2 : slot / 2; }
 
     // K-panel input descriptor for one GEMM
     struct KIn {
         int slot, kcount;
         // weight source for rows (n index) r and columns c of this K panel:
-        //   element = src_base + (row0 + r) * row_stride + c * col_stride
+        //   element = src_base + r * row_stride + c * col_stride
         int64_t src_base;
         int row_stride, col_stride;
         int valid_cols;
@@ -52,8 +52,8 @@ struct Builder {
         else j.ready_bar = (uint8_t)(TC_BAR_READY + grp);
     }
 
-    // Emit the MMA ops of one accumulator block.
-    void emit_block(const std::vector<KIn> &kin, int acc, int n_mma, int row0, int valid_rows) {
+    // Emit the MMA ops of one GEMM (one op per 64-wide K panel, full N) into accumulator set `acc`.
+    void emit_ops(const std::vector<KIn> &kin, int acc, int n_mma, int valid_rows) {
         for (size_t i = 0; i < kin.size(); ++i) {
             const KIn &k = kin[i];
             MmaOp op;
@@ -79,7 +79,7 @@ struct Builder {
             PackChunk pc;
             pc.dst_off = prog.wpack_bytes;
             pc.n_rows = n_mma;
-            pc.src_base = k.src_base + (int64_t)row0 * k.row_stride;
+            pc.src_base = k.src_base;
             pc.row_stride = k.row_stride;
             pc.col_stride = k.col_stride;
             pc.valid_rows = valid_rows < 0 ? 0 : (valid_rows > n_mma ? n_mma : valid_rows);
@@ -89,13 +89,13 @@ struct Builder {
         }
     }
 
-    // Hidden-panel K inputs: panels [0, n_panels) of the current activation, weight columns
+    // Hidden-panel K inputs: panels [0, n_panels) of the current activation (slots 0..), weight columns
     // start at col0 (in units of the logical matrix's K index), `valid` K entries in total.
     void hidden_kin(std::vector<KIn> &kin, int n_panels, int64_t src_base, int row_stride, int col_stride, int col0,
                     int valid) {
         for (int p = 0; p < n_panels; ++p) {
             KIn k;
-            k.slot = slot_of(p, par);
+            k.slot = p;
             k.kcount = 4;
             k.src_base = src_base + (int64_t)(col0 + 64 * p) * col_stride;
             k.row_stride = row_stride;
@@ -106,35 +106,35 @@ struct Builder {
         }
     }
 
-    // A GEMM whose output is a full hidden activation (n_out_panels panels), split in <=128-column
-    // blocks; block 0 goes to the other parity buffer, block 1 in place.
-    // out_row_src(r) = src row index of output row r is row0_src + r (valid n_valid rows).
+    // A GEMM whose output is a hidden activation of n_out_panels panels, written IN PLACE over the
+    // panels it read (safe: its epilogue starts only after all of its MMAs have completed, and the next
+    // GEMM accumulates into the other TMEM set). The epilogue runs as one job per 128-column block so
+    // that the next GEMM can start on panels 0,1 while block 1 is still being converted.
     void emit_hidden_gemm(const std::vector<KIn> &kin, int n_out_panels, int n_valid, uint8_t kind, uint32_t bias_off,
                           int save_slot0, int mask_slot, uint8_t enc, int enc_save_slot, bool consumed) {
         const int nblocks = n_out_panels > 2 ? 2 : 1;
-        const int newpar = par ^ 1;
-        for (int b = 0; b < nblocks; ++b) {
-            const int p0 = 2 * b;
-            const int pn = (n_out_panels - p0) > 2 ? 2 : (n_out_panels - p0);
-            emit_block(kin, b, 64 * pn, 128 * b, n_valid - 128 * b);
-        }
+        const int acc = set;
+        set ^= 1;
+        emit_ops(kin, acc, 64 * n_out_panels, n_valid);
         for (int b = 0; b < nblocks; ++b) {
             const int p0 = 2 * b;
             const int pn = (n_out_panels - p0) > 2 ? 2 : (n_out_panels - p0);
             EpiJob j;
             memset(&j, 0, sizeof(j));
             j.kind = kind;
-            j.acc = (uint8_t)b;
+            j.acc = (uint8_t)acc;
             j.ncols = (uint8_t)(64 * pn);
-            j.out_slot = (uint8_t)slot_of(p0, newpar);
+            j.out_slot = (uint8_t)p0;
             j.ready_bar = TC_NONE;
             j.enc = ENC_NONE;
             j.enc_bar = TC_NONE;
+            j.flags = (uint8_t)((b == 0 ? TC_JOB_WAIT_ACC : 0u) | (b == nblocks - 1 ? TC_JOB_RELEASE_ACC : 0u));
             j.save_slot = (int16_t)(save_slot0 < 0 ? -1 : save_slot0 + p0);
             j.enc_save_slot = -1;
             j.mask_slot = (int16_t)mask_slot;
             j.mask_word0 = (uint16_t)(4 * b);
-            j.bias_off = bias_off + 128u * b;
+            j.bias_off = (uint16_t)(bias_off + 128u * b);
+            j.acc_col = (uint16_t)(acc * 256 + 128 * b);
             if (consumed) signal(j.out_slot, j, false);
             if (b == 0 && enc != ENC_NONE) {
                 j.enc = enc;
@@ -143,11 +143,12 @@ struct Builder {
             }
             prog.jobs.push_back(j);
         }
-        par = newpar;
     }
 
-    void emit_small_gemm(const std::vector<KIn> &kin, int acc, int valid_rows, uint8_t kind, uint32_t bias_off) {
-        emit_block(kin, acc, 16, 0, valid_rows);
+    void emit_small_gemm(const std::vector<KIn> &kin, int valid_rows, uint8_t kind, uint32_t bias_off) {
+        const int acc = set;
+        set ^= 1;
+        emit_ops(kin, acc, 16, valid_rows);
         EpiJob j;
         memset(&j, 0, sizeof(j));
         j.kind = kind;
@@ -157,8 +158,10 @@ struct Builder {
         j.ready_bar = TC_NONE;
         j.enc = ENC_NONE;
         j.enc_bar = TC_NONE;
+        j.flags = TC_JOB_WAIT_ACC | TC_JOB_RELEASE_ACC;
         j.save_slot = j.enc_save_slot = j.mask_slot = -1;
-        j.bias_off = bias_off;
+        j.bias_off = (uint16_t)bias_off;
+        j.acc_col = (uint16_t)(acc * 256);
         prog.jobs.push_back(j);
     }
 
@@ -247,11 +250,11 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
             B.emit_hidden_gemm(kin, np, g.W, EK_RELU, bias_l[l], train ? sl.H(l) : -1, train ? (l - 1) : -1, ENC_NONE, -1,
                                true);
         }
-        {   // fc8 sigma row (out row 0), accumulator block 1, before the feature blocks
+        {   // fc8 sigma row (out row 0) as its own N=16 GEMM, issued before the feature GEMM rewrites h7 in place
             const LayerGeom &L = g.L[7];
             std::vector<Builder::KIn> kin;
             B.hidden_kin(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
-            B.emit_small_gemm(kin, 1, 1, EK_SIGMA, bias_s);
+            B.emit_small_gemm(kin, 1, EK_SIGMA, bias_s);
         }
         if (g.use_rgb_head) {
             {   // fc8 features: out rows 1..W, no activation
@@ -272,13 +275,13 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 const LayerGeom &L = g.L[9];
                 std::vector<Builder::KIn> kin;
                 B.hidden_kin(kin, np2, L.w_off, L.in_dim, 1, 0, g.W2);
-                B.emit_small_gemm(kin, 1, 4, EK_RGBA, bias_10);
+                B.emit_small_gemm(kin, 4, EK_RGBA, bias_10);
             }
         } else {
             // sigma-only network: nothing consumes h7 after the sigma GEMM
         }
         if (!B.err.empty()) { err = B.err; return false; }
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 3; ++i)
             if (B.pending[i]) { err = "schedule error: unconsumed ready event at tile end (fwd)"; return false; }
     }
 
@@ -319,7 +322,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
             B.emit_hidden_gemm(kin, np, g.W, EK_DMASK, 0, sl.dP(l - 1), l - 2, ENC_NONE, -1, /*consumed=*/l > 2);
         }
         if (!B.err.empty()) { err = B.err; return false; }
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 3; ++i)
             if (B.pending[i]) { err = "schedule error: unconsumed ready event at tile end (bwd)"; return false; }
     }
 

@@ -16,8 +16,8 @@ from nerf_rs_b200 import _lib
 MMA_OP = np.dtype([("w_off", "<u4"), ("n", "<u2"), ("a_slot", "u1"), ("acc", "u1"), ("flags", "u1"), ("wait0", "u1"),
                    ("wait1", "u1"), ("kcount", "u1")])
 EPI_JOB = np.dtype([("kind", "u1"), ("acc", "u1"), ("ncols", "u1"), ("out_slot", "u1"), ("ready_bar", "u1"), ("enc", "u1"),
-                    ("enc_bar", "u1"), ("pad0", "u1"), ("save_slot", "<i2"), ("enc_save_slot", "<i2"), ("mask_slot", "<i2"),
-                    ("mask_word0", "<u2"), ("bias_off", "<u4")])
+                    ("enc_bar", "u1"), ("flags", "u1"), ("save_slot", "<i2"), ("enc_save_slot", "<i2"), ("mask_slot", "<i2"),
+                    ("mask_word0", "<u2"), ("bias_off", "<u2"), ("acc_col", "<u2")])
 PACK_CHUNK = np.dtype([("dst_off", "<u4"), ("n_rows", "<i4"), ("src_base", "<i8"), ("row_stride", "<i4"),
                        ("col_stride", "<i4"), ("valid_rows", "<i4"), ("valid_cols", "<i4")])
 WGRAD_UNIT = np.dtype([("n_p", "u1"), ("n_q", "u1"), ("pad", "u1", (2,)), ("p_slot", "<i2", (4,)), ("q_slot", "<i2", (4,)),
@@ -29,9 +29,11 @@ NONE = 0xFF
 OP_FIRST, OP_COMMIT = 1, 2
 (EK_PROLOGUE_FWD, EK_RELU, EK_LINEAR, EK_SIGMA, EK_RGBA, EK_PROLOGUE_BWD, EK_DMASK, EK_DCOPY) = range(8)
 ENC_NONE, ENC_X, ENC_D, ENC_DSIGMA = range(4)
-NUM_STAGES = 7
-BAR_FULL, BAR_EMPTY, BAR_ACC_FULL, BAR_ACC_FREE, BAR_READY = 0, 7, 14, 16, 18
-SLOT_E = 6
+NUM_STAGES = 4
+BAR_FULL, BAR_EMPTY, BAR_ACC_FULL, BAR_ACC_FREE, BAR_READY = 0, 4, 8, 10, 12
+SLOT_E = 4
+NUM_SLOTS = 5
+JOB_WAIT, JOB_RELEASE = 1, 2
 
 
 def get_plan(cfg, program):
@@ -81,8 +83,8 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
     inputs. Returns dict(sigma, rgba, act{slot: panel}, grad{slot: panel}, masks{slot: [128,256] bool})."""
     ops, jobs, chunks = plan["ops"], plan["jobs"], plan["chunks"]
     bias = padded_bias(plan, params)
-    slots = np.zeros((7, 128, 64), dtype=np.float32)
-    acc = np.zeros((2, 128, 128), dtype=np.float32)
+    slots = np.zeros((NUM_SLOTS, 128, 64), dtype=np.float32)
+    acc = np.zeros((128, 512), dtype=np.float32)   # TMEM columns: two 256-column accumulator sets
     out = dict(sigma=None, rgba=None, saved={}, masks={} if masks is None else masks)
 
     def pad(a, w):
@@ -94,7 +96,8 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
         k = j["kind"]
         if k in (EK_RELU, EK_LINEAR, EK_DMASK, EK_DCOPY):
             nc = int(j["ncols"])
-            v = acc[j["acc"]][:, :nc].copy()
+            c0 = int(j["acc_col"])
+            v = acc[:, c0:c0 + nc].copy()
             if k in (EK_RELU, EK_LINEAR):
                 v = v + bias[j["bias_off"]:j["bias_off"] + nc][None, :]
             if k == EK_RELU:
@@ -110,9 +113,10 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
                 if j["save_slot"] >= 0:
                     out["saved"][int(j["save_slot"]) + p] = slots[j["out_slot"] + p].copy()
         elif k == EK_SIGMA:
-            out["sigma"] = acc[j["acc"]][:, 0] + bias[j["bias_off"]]
+            out["sigma"] = acc[:, int(j["acc_col"])] + bias[j["bias_off"]]
         elif k == EK_RGBA:
-            out["rgba"] = 1.0 / (1.0 + np.exp(-(acc[j["acc"]][:, :4] + bias[j["bias_off"]:j["bias_off"] + 4][None, :])))
+            c0 = int(j["acc_col"])
+            out["rgba"] = 1.0 / (1.0 + np.exp(-(acc[:, c0:c0 + 4] + bias[j["bias_off"]:j["bias_off"] + 4][None, :])))
         wrote_e = True
         if k == EK_PROLOGUE_FWD or j["enc"] == ENC_X:
             slots[SLOT_E] = pad(posenc_x, 64)
@@ -138,13 +142,18 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
         kk = 16 * int(op["kcount"])
         prod = slots[op["a_slot"]][:, :kk] @ w[:, :kk].T
         n = int(op["n"])
+        c0 = 256 * int(op["acc"])
         if op["flags"] & OP_FIRST:
-            acc[op["acc"]][:, :n] = prod
+            acc[:, c0:c0 + n] = prod
         else:
-            acc[op["acc"]][:, :n] += prod
+            acc[:, c0:c0 + n] += prod
         if op["flags"] & OP_COMMIT:
-            assert jobs[ji]["acc"] == op["acc"], "job/commit order mismatch"
-            run_job(jobs[ji]); ji += 1
+            assert jobs[ji]["acc"] == op["acc"] and jobs[ji]["flags"] & JOB_WAIT, "job/commit order mismatch"
+            while True:   # all jobs of this GEMM, then any prologue-type jobs
+                last = jobs[ji]["flags"] & JOB_RELEASE
+                run_job(jobs[ji]); ji += 1
+                if last:
+                    break
             while ji < len(jobs) and jobs[ji]["acc"] == NONE:
                 run_job(jobs[ji]); ji += 1
     assert ji == len(jobs)
@@ -187,10 +196,10 @@ def simulate_protocol(plan, n_tiles, rng, max_steps=2_000_000):
     protocol of k_chain. Raises AssertionError on deadlock, on a read of a stale or too-new slot
     version, on an accumulator or ring-stage hazard. Returns the number of scheduler steps."""
     ops, jobs = plan["ops"], plan["jobs"]
-    bars = [Barrier(1) for _ in range(2 * NUM_STAGES)] + [Barrier(1), Barrier(1), Barrier(4), Barrier(4)] + [Barrier(4) for _ in range(4)]
+    bars = [Barrier(1) for _ in range(2 * NUM_STAGES)] + [Barrier(1), Barrier(1), Barrier(4), Barrier(4)] + [Barrier(4) for _ in range(3)]
 
     # ---- logical (sequential) semantics: expected slot / accumulator versions per op and job
-    slot_ver = [0] * 7
+    slot_ver = [0] * NUM_SLOTS
     acc_ver = [0, 0]
     op_expect, job_expect_acc, job_writes = [], [], []
     seq = []  # (tile, 'op'/'job', index)
@@ -217,13 +226,17 @@ def simulate_protocol(plan, n_tiles, rng, max_steps=2_000_000):
                 acc_ver[op["acc"]] += 1
             op_expect.append((slot_ver[op["a_slot"]], acc_ver[op["acc"]]))
             if op["flags"] & OP_COMMIT:
-                logical_job(ji); ji += 1
+                while True:
+                    last = jobs[ji]["flags"] & JOB_RELEASE
+                    logical_job(ji); ji += 1
+                    if last:
+                        break
                 while ji < len(jobs) and jobs[ji]["acc"] == NONE:
                     logical_job(ji); ji += 1
         assert ji == len(jobs)
 
     # ---- concurrent state
-    cur_slot_ver = [0] * 7
+    cur_slot_ver = [0] * NUM_SLOTS
     cur_acc_ver = [0, 0]       # version being accumulated / last written
     stage_content = [None] * NUM_STAGES    # global op index whose chunk is in the stage (after load completes)
     n_total_ops = n_tiles * len(ops)
@@ -261,7 +274,7 @@ def simulate_protocol(plan, n_tiles, rng, max_steps=2_000_000):
         # epilogue
         if epi["i"] < n_total_jobs:
             j = jobs[epi["i"] % len(jobs)]
-            if epi["sub"] == 0 and j["acc"] != NONE:
+            if epi["sub"] == 0 and j["acc"] != NONE and (j["flags"] & JOB_WAIT):
                 if bars[BAR_ACC_FULL + j["acc"]].passed((epi["aph"] >> int(j["acc"])) & 1):
                     actions.append("epi")
             else:
@@ -315,7 +328,8 @@ def simulate_protocol(plan, n_tiles, rng, max_steps=2_000_000):
             j = jobs[gj % len(jobs)]
             if epi["sub"] == 0:
                 if j["acc"] != NONE:
-                    epi["aph"] ^= 1 << int(j["acc"])
+                    if j["flags"] & JOB_WAIT:
+                        epi["aph"] ^= 1 << int(j["acc"])
                     assert cur_acc_ver[j["acc"]] == job_expect_acc[gj], f"job {gj}: accumulator version mismatch"
                     assert not any(o["acc"] == j["acc"] and o["acc_ver"] == job_expect_acc[gj] for o in inflight), "job reads an accumulator with MMAs in flight"
                     epi["sub"] = 1
@@ -323,7 +337,8 @@ def simulate_protocol(plan, n_tiles, rng, max_steps=2_000_000):
                     epi["sub"] = 2
             elif epi["sub"] == 1:   # accumulator read: release it
                 assert cur_acc_ver[j["acc"]] == job_expect_acc[gj], "accumulator overwritten while the epilogue was reading it"
-                bars[BAR_ACC_FREE + j["acc"]].arrive(4)
+                if j["flags"] & JOB_RELEASE:
+                    bars[BAR_ACC_FREE + j["acc"]].arrive(4)
                 epi["sub"] = 2
             elif epi["sub"] == 2:   # panel writes
                 for slot, ver in job_writes[gj]:

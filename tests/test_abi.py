@@ -1,0 +1,76 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/*.h declares
+(no compute calls without a GPU), and the product refuses to run without one."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import nerf_rs_b200 as nb
+from nerf_rs_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    names = set()
+    for fn in os.listdir(os.path.join(ROOT, "include")):
+        if fn.endswith(".h"):
+            src = open(os.path.join(ROOT, "include", fn)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names |= set(re.findall(r"\b(nerf_[a-z0-9_]+)\s*\(", src))
+    return names
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    lib = nb.load()
+    declared = _declared()
+    assert len(declared) >= 35
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.nerf_abi_version() == 1
+
+
+def test_config_struct_matches_header():
+    cfg = nb.default_config()
+    assert cfg.struct_size == ctypes.sizeof(nb.NerfConfig) == 18 * 4
+    assert (cfg.image_w, cfg.num_rays, cfg.num_samples, cfg.hidden, cfg.xyz_freqs, cfg.dir_freqs, cfg.skip_layer) == (800, 4096, 64, 256, 10, 4, 5)
+    assert abs(cfg.learning_rate - 5e-4) < 1e-9          # cli.rs:64-65
+    s = nb.as_shipped_config()
+    assert (s.image_w, s.num_rays, s.num_samples, s.hidden, s.xyz_freqs, s.dir_freqs, s.use_rgb_head) == (128, 84, 64, 100, 0, -1, 0)
+
+
+def test_error_strings_and_null_handling():
+    lib = nb.load()
+    assert lib.nerf_strerror(0) == b"ok"
+    assert b"no CPU fallback" in lib.nerf_strerror(_lib.ERR_NO_DEVICE)
+    assert lib.nerf_default_config(None) == _lib.ERR_INVALID_ARG
+    assert lib.nerf_destroy(None) == 0
+    assert lib.nerf_num_params(None) == 0
+
+
+def test_no_gpu_means_no_product():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nb.NerfError) as e:
+        nb.NeRF(nb.default_config())
+    assert e.value.status == _lib.ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    import subprocess
+    import sys
+    code = "import sys; import nerf_rs_b200; nerf_rs_b200.load(); print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+    assert out == "False"
+    for fn in os.listdir(os.path.join(ROOT, "nerf_rs_b200")):
+        if fn.endswith(".py"):
+            assert "oracle" not in open(os.path.join(ROOT, "nerf_rs_b200", fn)).read().replace("no CPU fallback", "").lower().replace("the oracle", "") or fn == "__init__.py"
+
+
+def test_view_angle_grid_matches_oracle():
+    from oracle import ray_c
+    for n in (1, 2, 6):
+        assert nb.get_view_angles(n).tobytes() == ray_c.get_view_angles(n).tobytes()

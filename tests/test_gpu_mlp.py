@@ -127,25 +127,60 @@ def test_predict_asserts_like_the_reference():
         nb.Trainer(m).step(out, gold[:-4])
 
 
-def test_loss_curve_1k_steps_within_2_percent():
-    """North-star gate: loss curves over 1k steps stay within 2% of the reference arithmetic."""
-    kw = dict(hidden=64, num_rays=32, num_samples=32)
-    cfg = nb.default_config(image_w=100, image_h=100, mlp_impl=_lib.MLP_TCGEN05, **kw)
+def _train_curves(cfg, fixed_batch, steps, seed):
     m = nb.NeRF(cfg)
     mcfg = G.model_cfg(cfg)
     params_t = M.init_params(mcfg, 3)
     m.set_weights(M.flatten_params(params_t).numpy())
-    pts, t, dirs, gold = G.make_points(cfg.num_rays, cfg.num_samples, 9)
     tr = M.Trainer(mcfg, params_t, lr=5e-4)
     trn = nb.Trainer(m, 5e-4)
-    tp, tt, td, tg = torch.from_numpy(pts), torch.from_numpy(t), torch.from_numpy(dirs), torch.from_numpy(gold)
     ref, got = [], []
-    for it in range(1000):
-        o, _ = tr.predict(tp, tt, cfg.num_rays, cfg.num_samples, td, literal=False)
-        ref.append(tr.step(o, tg))
+    for it in range(steps):
+        pts, t, dirs, gold = G.make_points(cfg.num_rays, cfg.num_samples, seed if fixed_batch else seed + it)
+        if not fixed_batch:   # smooth target: a function of the ray direction, so fresh rays are learnable
+            gold = np.repeat(0.5 + 0.5 * np.tanh(3 * dirs[:, :1]), 4, axis=1).reshape(-1).astype(np.float32)
+        o, _ = tr.predict(torch.from_numpy(pts), torch.from_numpy(t), cfg.num_rays, cfg.num_samples, torch.from_numpy(dirs), literal=False)
+        ref.append(tr.step(o, torch.from_numpy(gold)))
         out, _ = m.predict(pts, t, dirs.reshape(-1), train=True, want_sigma=False)
         got.append(trn.step(out, gold))
-    ref, got = np.array(ref), np.array(got)
-    assert got[-1] < got[0] * 0.8                      # it actually trains
+    return np.array(ref), np.array(got)
+
+
+def test_loss_curve_1k_steps_within_2_percent():
+    """North-star gate: loss curves over 1k steps stay within 2% of the reference arithmetic
+    (fp32 torch oracle), fresh rays every step; curves compared after a 50-step moving average."""
+    cfg = nb.default_config(image_w=100, image_h=100, mlp_impl=_lib.MLP_TCGEN05, hidden=64, num_rays=64, num_samples=32)
+    ref, got = _train_curves(cfg, False, 1000, 100)
+    k = np.ones(50) / 50
+    rs, gs = np.convolve(ref, k, "valid"), np.convolve(got, k, "valid")
+    assert gs[-1] < 0.5 * gs[0]                            # it actually trains
+    assert np.abs(gs - rs).max() <= 0.02 * rs.max()         # within 2% of the curve's scale everywhere
+    assert np.all(np.abs(gs - rs) <= 0.02 * rs + 2e-5)      # and within 2% pointwise (+ bf16 noise floor)
+
+
+def test_fixed_batch_overfit_curve_tracks_reference():
+    cfg = nb.default_config(image_w=100, image_h=100, mlp_impl=_lib.MLP_TCGEN05, hidden=64, num_rays=32, num_samples=32)
+    ref, got = _train_curves(cfg, True, 300, 9)
+    assert got[-1] < got[0] * 0.8
     assert np.abs(got - ref).max() <= 0.02 * ref.max()
-    assert np.abs(got[-100:].mean() - ref[-100:].mean()) <= 0.02 * ref[-100:].mean()
+
+
+def test_step_is_reproducible():
+    """Same state, same batch, 20 repetitions: gradients may differ only by fp32 atomic-add ordering.
+    (A synchronisation bug in the fused kernels shows up here as an occasional large deviation.)"""
+    m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup("ns256_big", _lib.MLP_TCGEN05)
+    w0 = M.flatten_params(params_t).numpy()
+    grads, outs = [], []
+    for rep in range(20):
+        m.set_weights(w0)
+        m.set_adam_state(np.zeros_like(w0), np.zeros_like(w0), 0)
+        out, sig = _predict(m, cfg, pts, t, dirs, train=True)
+        nb.Trainer(m, 5e-4).step(out, gold)
+        grads.append(m.get_grads())
+        outs.append((out, sig))
+    for out, sig in outs[1:]:
+        assert np.array_equal(out, outs[0][0]) and np.array_equal(sig, outs[0][1])   # forward is deterministic
+    g0 = grads[0]
+    scale = np.abs(g0).max()
+    for g in grads[1:]:
+        assert np.abs(g - g0).max() <= 2e-5 * scale

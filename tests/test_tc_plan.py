@@ -98,7 +98,7 @@ def test_chunk_stream_is_contiguous_and_bounded():
         off = 0
         for op, pc in zip(p["ops"], p["chunks"]):
             assert op["w_off"] == off == pc["dst_off"]
-            assert op["n"] % 16 == 0 and 16 <= op["n"] <= 128 and op["n"] * 128 <= 16384
+            assert op["n"] % 16 == 0 and 16 <= op["n"] <= 256 and op["n"] * 128 <= 32768
             assert 1 <= op["kcount"] <= 4
             off += int(op["n"]) * 128
         assert off == p["wpack_bytes"]
