@@ -36,6 +36,23 @@ N_VIEW_GRID = 6          # get_view_angles(6) -> 84 (yaw,pitch) pairs, the refer
 FWD_FLOP = 2 * 528000    # per sample, W=256
 DGRAD_FLOP = 2 * 492288
 WGRAD_FLOP = 2 * 528000
+# algorithmic (unpadded) HBM bytes per sample, DESIGN.md section 4
+ACT_BYTES = 2 * (63 + 27 + 7 * 256 + 256 + 128)     # bf16 activations saved by the forward (wgrad M-side operand)
+GRAD_BYTES = 2 * (4 + 1 + 128 + 256 + 7 * 256)      # bf16 pre-activation gradients saved by dgrad (wgrad N-side operand)
+COMPOSITE_FWD_BYTES, COMPOSITE_BWD_BYTES, SAMPLE_BYTES, ADAM_BYTES_PER_PARAM = 24, 44, 16, 28
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the MLP kernels from the committed `ncu --set full` capture (profiles/)."""
+    import glob
+    out = {}
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json"))):
+        for k in json.load(open(f)).get("kernels", []):
+            nm = {"k_chain<0, 1>": "mlp_fwd_train", "k_chain<1, 1>": "mlp_dgrad", "k_wgrad": "mlp_wgrad", "k_chain<0, 0>": "mlp_fwd",
+                  "k_chain2<0, 1>": "mlp_fwd_train", "k_chain2<1, 1>": "mlp_dgrad", "k_chain2<0, 0>": "mlp_fwd"}.get(k["kernel"])
+            if nm and "dram_traffic_bytes" in k:
+                out[nm] = {"bytes": k["dram_traffic_bytes"], "source": os.path.basename(f)}
+    return out
 
 
 def peaks():
@@ -135,8 +152,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--samples", type=int, default=S)
@@ -192,7 +209,6 @@ def main():
     ms = model.timer_stop()
     launches = model.launch_count - launches0
     barrier()
-    sampler.stop_flag = True
     loss = model.last_loss()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -201,27 +217,48 @@ def main():
     value = world * rays * args.steps / (ms_max * 1e-3)
 
     # ---- per-kernel durations (separate pass, events around every launch on the library stream)
+    prof_steps = min(args.steps, 100)
     model.profile(True)
-    for it in range(args.steps):
+    for it in range(prof_steps):
         model.train_iter(5000 + it)
     prof = model.profile_read()
     model.profile(False)
+    sampler.stop_flag = True
     nsamp = rays * samples
     hbm, tf_burst, tf_sus, how = peaks()
-    kern = {k: {"ms": v[0] / max(1, v[1]), "launches_per_step": v[1] / args.steps} for k, v in prof.items()}
-    step_prof_ms = sum(v[0] for v in prof.values()) / args.steps
-
-    def tfl(name, flop):
-        return flop * nsamp / (kern[name]["ms"] * 1e-3) / 1e12 if name in kern and kern[name]["ms"] > 0 else None
-    mlp = {"mlp_fwd_train": tfl("mlp_fwd_train", FWD_FLOP), "mlp_dgrad": tfl("mlp_dgrad", DGRAD_FLOP), "mlp_wgrad": tfl("mlp_wgrad", WGRAD_FLOP)}
-    mlp_ms = sum(kern[k]["ms"] for k in mlp if k in kern)
+    kern = {k: {"ms": v[0] / max(1, v[1]), "launches_per_step": v[1] / prof_steps} for k, v in prof.items()}
+    step_prof_ms = sum(v[0] for v in prof.values()) / prof_steps
+    n_params = model.num_params
+    # work per launch of each kernel: (bound, algorithmic units) -- FLOP for tensor-bound, bytes for HBM-bound
+    work = {
+        "mlp_fwd_train": ("tensor", FWD_FLOP * nsamp), "mlp_dgrad": ("tensor", DGRAD_FLOP * nsamp),
+        "mlp_wgrad": ("hbm", (ACT_BYTES + GRAD_BYTES) * nsamp),
+        "sample": ("hbm", SAMPLE_BYTES * nsamp), "composite_fwd": ("hbm", COMPOSITE_FWD_BYTES * nsamp),
+        "composite_bwd": ("hbm", COMPOSITE_BWD_BYTES * nsamp), "adam": ("hbm", ADAM_BYTES_PER_PARAM * n_params),
+    }
+    traffic = ncu_traffic() if (rays, samples) == (R, S) else {}
+    per_kernel = {}
+    for k, (bound, units) in work.items():
+        if k not in kern or kern[k]["ms"] <= 0:
+            continue
+        sec = kern[k]["ms"] * 1e-3
+        if bound == "tensor":
+            ach, peak, unit = units / sec / 1e12, tf_sus, "TFLOP/s"
+        else:
+            ach, peak, unit = units / sec / 1e9, hbm, "GB/s"
+        per_kernel[k] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "ms": round(kern[k]["ms"], 4),
+                         "share_of_step": kern[k]["ms"] * kern[k]["launches_per_step"] / step_prof_ms,
+                         "traffic": traffic.get(k, {}).get("bytes")}
+    if "mlp_wgrad" in per_kernel:   # the same kernel against the tensor roof, for reference
+        per_kernel["mlp_wgrad"]["tflops"] = WGRAD_FLOP * nsamp / (kern["mlp_wgrad"]["ms"] * 1e-3) / 1e12
+    mlp_ms = sum(kern[k]["ms"] for k in ("mlp_fwd_train", "mlp_dgrad", "mlp_wgrad") if k in kern)
     mlp_all = (FWD_FLOP + DGRAD_FLOP + WGRAD_FLOP) * nsamp / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
-    dom = max((k for k in mlp if k in kern), key=lambda k: kern[k]["ms"], default=None)
-    roofline = {"bound": "tensor", "kernel": dom, "achieved": mlp.get(dom), "peak": tf_sus, "unit": "TFLOP/s",
-                "frac": (mlp[dom] / tf_sus) if dom and mlp.get(dom) else None, "traffic": None, "peak_source": how + " (sustained)",
-                "share_of_step": kern[dom]["ms"] / step_prof_ms if dom else None,
-                "mlp_fwd_bwd_tflops": mlp_all, "per_kernel_tflops": mlp,
-                "kernel_ms": {k: round(v["ms"], 4) for k, v in kern.items()}}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["share_of_step"], default=None)
+    roofline = dict(per_kernel[dom]) if dom else {"bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
+    roofline.update({"kernel": dom, "peak_source": how + (" (sustained: kernel timed inside a long step)" if dom and per_kernel[dom]["bound"] == "tensor" else " (copy)"),
+                     "mlp_fwd_dgrad_wgrad_tflops": mlp_all, "mlp_frac_of_tensor_peak": (mlp_all / tf_sus) if mlp_all else None,
+                     "kernels": per_kernel,
+                     "kernel_ms": {k: round(v["ms"], 4) for k, v in kern.items()}})
 
     # ---- inference / render throughput (forward only, no saved activations)
     model.profile(True)
@@ -236,7 +273,8 @@ def main():
         tot = sum(v[0] for v in pr.values()) / 5
         render = {"msamples_per_sec": nsamp / (tot * 1e-3) / 1e6, "mlp_fwd_ms": fwd_ms,
                   "mlp_fwd_tflops": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12,
-                  "mlp_fwd_frac_of_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_burst}
+                  "mlp_fwd_frac_of_sustained_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_sus,
+                  "mlp_fwd_frac_of_burst_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_burst}
 
     # ---- end to end through the reference-facing calls with host buffers
     from tests import gpu_util as G
@@ -244,7 +282,7 @@ def main():
     pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
     pts, tt, dirs_f, gold = pin(pts), pin(tt), pin(dirs.reshape(-1).copy()), pin(gold)
     trainer = nb.Trainer(model)
-    e2e_steps = max(3, min(args.steps, 30))
+    e2e_steps = max(3, min(args.steps, 200))
     for it in range(3):
         out, _ = model.predict(pts, tt, dirs_f, train=True, want_sigma=False)
         trainer.step(out, gold)
@@ -266,9 +304,9 @@ def main():
         return
     cpu = None
     if not args.no_cpu:
-        v, cms = cpu_reference(3, 1)
+        v, cms = cpu_reference(10, 1)
         cpu = {"value": v, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "ms_per_step": cms,
-               "sample": f"3 full steps of {R}x{S} (restated tch path: torch CPU + C sampler) after 1 warm-up"}
+               "sample": f"10 full steps of {R}x{S} (restated tch path: torch CPU + C sampler) after 1 warm-up"}
     line = {
         "metric": "training_rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -276,7 +314,7 @@ def main():
         "config": {"workload": f"{IMG}x{IMG} synthetic, {rays} rays x {samples} samples/step training per GPU, 8x{W} MLP, posenc 10/4 (BASELINE configs[1])",
                    "views": int(n_views), "parallelism": f"dp{world}", "global_rays_per_step": world * rays,
                    "cache": "per-step working set (saved activations + gradients, ~2.4 GB) exceeds the 126 MB L2"},
-        "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "clocks": dict(sampler.summary(), window="timed steps + the per-kernel event pass over the same steps"), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu, "render": render, "final_loss": loss,
     }
     print(json.dumps(line))
