@@ -45,9 +45,11 @@ extern "C" {
 #define NERF_DEPTH_STRATIFIED 1  /* t = ((i + u) / S) * 2.0 (north-star stratified option) */
 
 /* MLP implementations */
-#define NERF_MLP_TCGEN05 0  /* fused tcgen05/TMEM kernels (the product path) */
+#define NERF_MLP_TCGEN05 0  /* fused tcgen05/TMEM kernels (the product path): CTA pairs (cta_group::2), two tiles in flight */
 #define NERF_MLP_SIMT 1     /* plain CUDA-core kernels with the same bf16 rounding points;
                                on-device cross-check for sizes the CPU oracle cannot reach */
+#define NERF_MLP_SIMT_FP32 2   /* the same without any bf16 rounding */
+#define NERF_MLP_TCGEN05_V1 3  /* first-generation tcgen05 chain (one tile per CTA, cta_group::1), kept for A/B runs */
 
 typedef struct nerf_ctx nerf_ctx;
 

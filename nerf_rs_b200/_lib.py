@@ -13,7 +13,7 @@ _lib = None
 NERF_OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_COMM, ERR_STATE, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 DEPTH_REFERENCE, DEPTH_STRATIFIED = 0, 1
-MLP_TCGEN05, MLP_SIMT, MLP_SIMT_FP32 = 0, 1, 2
+MLP_TCGEN05, MLP_SIMT, MLP_SIMT_FP32, MLP_TCGEN05_V1 = 0, 1, 2, 3
 
 
 class NerfConfig(ctypes.Structure):

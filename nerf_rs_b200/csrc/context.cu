@@ -21,6 +21,8 @@
 
 namespace {
 
+inline bool is_tc(int impl) { return impl == NERF_MLP_TCGEN05 || impl == NERF_MLP_TCGEN05_V1; }
+
 struct Profiler {
     bool on = false;
     std::vector<std::string> names;
@@ -265,7 +267,7 @@ int ensure_packed(nerf_ctx *c) {
 int mlp_forward(nerf_ctx *c, int r0, int nr, int train) {
     const int64_t n = (int64_t)nr * c->S;
     const int64_t s0 = (int64_t)r0 * c->S;
-    if (c->cfg.mlp_impl == NERF_MLP_TCGEN05) {
+    if (is_tc(c->cfg.mlp_impl)) {
         int rc = ensure_packed(c);
         if (rc) return rc;
         Scope s(c, train ? "mlp_fwd_train" : "mlp_fwd");
@@ -283,7 +285,7 @@ int mlp_forward(nerf_ctx *c, int r0, int nr, int train) {
 int mlp_backward(nerf_ctx *c, int r0, int nr) {
     const int64_t n = (int64_t)nr * c->S;
     const int64_t s0 = (int64_t)r0 * c->S;
-    if (c->cfg.mlp_impl == NERF_MLP_TCGEN05) {
+    if (is_tc(c->cfg.mlp_impl)) {
         if (tc_backward(c->tc, c->d_rgba + 4 * s0, c->d_dsigma + s0, c->d_drgba + 4 * s0, n, c->d_grads, c->stream,
                         prof_between, c))
             return fail(c, NERF_ERR_INVALID_ARG, tc_last_error(c->tc));
@@ -518,7 +520,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     if (prop.major != 10) return NERF_ERR_NO_DEVICE;  // kernels are built for sm_100a only
     if (cfg->num_rays < 1 || cfg->num_samples < 1 || cfg->num_samples > 256 || cfg->hidden < 2 || cfg->hidden > 256 ||
         cfg->xyz_freqs < 0 || cfg->xyz_freqs > 10 || cfg->dir_freqs > 4 || cfg->image_w < 1 || cfg->image_h < 1 ||
-        cfg->mlp_impl < 0 || cfg->mlp_impl > 2 || cfg->depth_mode < 0 || cfg->depth_mode > 1)
+        cfg->mlp_impl < 0 || cfg->mlp_impl > 3 || cfg->depth_mode < 0 || cfg->depth_mode > 1)
         return NERF_ERR_UNSUPPORTED;
     nerf_ctx *c = new nerf_ctx();
     c->cfg = *cfg;
@@ -580,10 +582,10 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     CUB(cudaMemsetAsync(c->d_drgba, 0, sizeof(float) * 4 * B, c->stream));
     CUB(cudaMemsetAsync(c->d_loss, 0, sizeof(float) * 4, c->stream));
     CUB(cudaMallocHost(&c->h_loss, sizeof(float) * 4));
-    if (cfg->mlp_impl == NERF_MLP_TCGEN05) {
+    if (is_tc(cfg->mlp_impl)) {
         std::string e;
         const int64_t max_tiles = ((int64_t)c->chunk * c->S + NERF_TILE_M - 1) / NERF_TILE_M;
-        c->tc = tc_create(c->g, max_tiles, c->num_sms, e);
+        c->tc = tc_create(c->g, max_tiles, c->num_sms, cfg->mlp_impl == NERF_MLP_TCGEN05_V1 ? 1 : 2, e);
         if (!c->tc) return bail(NERF_ERR_UNSUPPORTED, e);
     } else {
         const int64_t bc = (int64_t)c->chunk * c->S;

@@ -668,6 +668,9 @@ struct TcState {
     int64_t work_tiles = -1;
     uint8_t *d_act = nullptr, *d_grad = nullptr;
     uint32_t *d_mask = nullptr;
+    uint64_t bias_version = 1;   // bumped by tc_pack_weights (constant-bank copy of the biases, v2)
+    int version = 2;   // 2: CTA-pair two-lane chain (mlp_tc2.cu); 1: one tile per CTA (k_chain above)
+    Lane2Program *fwd_train2 = nullptr, *fwd_infer2 = nullptr, *bwd2 = nullptr;
     std::string err;
 };
 
@@ -684,11 +687,13 @@ static bool upload_program(const TcProgram &p, DevProgram &d, bool own_weights) 
     return d.ops && d.jobs;
 }
 
-TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, std::string &err) {
+TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version, std::string &err) {
     TcState *s = new TcState();
     s->g = g;
     s->num_sms = num_sms;
+    max_tiles = (max_tiles + 1) & ~(int64_t)1;   // the pair kernel walks 256-sample pair tiles
     s->max_tiles = max_tiles;
+    s->version = version;
     if (!tc_build_plan(g, s->plan, err)) { delete s; return nullptr; }
     for (const TcProgram *p : {&s->plan.fwd_train, &s->plan.fwd_infer, &s->plan.bwd}) {
         const size_t need = ((s->plan.bias_floats * 4 + 15) & ~15u) + ((p->ops.size() * sizeof(MmaOp) + 15) & ~15u) + p->jobs.size() * sizeof(EpiJob);
@@ -716,6 +721,17 @@ TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, std::string
         tc_destroy(s);
         return nullptr;
     }
+    if (version == 2) {
+        LaneProgram lp;
+        const TcProgram *src[3] = {&s->plan.fwd_train, &s->plan.fwd_infer, &s->plan.bwd};
+        Lane2Program **dst[3] = {&s->fwd_train2, &s->fwd_infer2, &s->bwd2};
+        for (int i = 0; i < 3; ++i) {
+            if (!make_lane_program(*src[i], lp, err) || !(*dst[i] = tc2_upload(lp, s->plan.bias_floats, err))) {
+                tc_destroy(s);
+                return nullptr;
+            }
+        }
+    }
     return s;
 }
 
@@ -736,6 +752,10 @@ void tc_destroy(TcState *s) {
     cudaFree(s->d_act);
     cudaFree(s->d_grad);
     cudaFree(s->d_mask);
+    tc2_bias_release(s);
+    tc2_free(s->fwd_train2);
+    tc2_free(s->fwd_infer2);
+    tc2_free(s->bwd2);
     delete s;
 }
 
@@ -749,6 +769,7 @@ void tc_pack_weights(TcState *s, const float *params, cudaStream_t st) {
     k_pack_chunks<<<s->fwd_train.n_chunks, 256, 0, st>>>(s->fwd_train.chunks, params, s->fwd_train.wpack);
     k_pack_chunks<<<s->bwd.n_chunks, 256, 0, st>>>(s->bwd.chunks, params, s->bwd.wpack);
     k_pack_bias<<<(int)s->plan.biases.size(), 128, 0, st>>>(s->d_pbias, (int)s->plan.biases.size(), params, s->d_bias);
+    ++s->bias_version;
 }
 
 int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, int S, int train, float *sigma, float *rgba,
@@ -757,6 +778,20 @@ int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, in
     if (n_tiles == 0) return 0;
     if (train && n_tiles > s->max_tiles) { s->err = "tc_forward: batch exceeds the saved-activation capacity"; return -1; }
     const DevProgram &P = train ? s->fwd_train : s->fwd_infer;
+    if (s->version == 2) {
+        Chain2Launch l;
+        memset(&l, 0, sizeof(l));
+        l.bwd = false; l.save = train != 0;
+        l.wpack = P.wpack; l.bias = s->d_bias; l.bias_floats = (int)s->plan.bias_floats;
+        l.bias_slot = tc2_bias_upload(s, s->bias_version, s->d_bias, (int)s->plan.bias_floats, st);
+        if (l.bias_slot < 0) { s->err = "tc_forward: bias table exceeds the constant-bank slot"; return -1; }
+        l.n_samples = n; l.S = S; l.xyz_freqs = s->g.xyz_freqs; l.dir_freqs = s->g.dir_freqs; l.num_sms = s->num_sms;
+        l.points = points; l.dirs = dirs; l.sigma = sigma; l.rgba = rgba;
+        l.save_base = train ? s->d_act : nullptr; l.save_slots = s->plan.act_slots;
+        l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
+        tc2_launch(train ? s->fwd_train2 : s->fwd_infer2, l, st);
+        return 0;
+    }
     ChainArgs a;
     memset(&a, 0, sizeof(a));
     a.ops = P.ops; a.jobs = P.jobs; a.n_ops = P.n_ops; a.n_jobs = P.n_jobs;
@@ -838,7 +873,18 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
     a.mask_base = s->d_mask; a.mask_slots = s->plan.mask_slots;
     const int grid = (int)(n_tiles < s->num_sms ? n_tiles : s->num_sms);
     if (between) between(user, "mlp_dgrad");
-    k_chain<true, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
+    if (s->version == 2) {
+        Chain2Launch l;
+        memset(&l, 0, sizeof(l));
+        l.bwd = true; l.save = true;
+        l.wpack = s->bwd.wpack; l.bias = s->d_bias; l.bias_floats = (int)s->plan.bias_floats;
+        l.n_samples = n; l.S = 1; l.xyz_freqs = s->g.xyz_freqs; l.dir_freqs = s->g.dir_freqs; l.num_sms = s->num_sms;
+        l.rgba = const_cast<float *>(rgba); l.d_sigma = d_sigma; l.d_rgba = d_rgba;
+        l.save_base = s->d_grad; l.save_slots = s->plan.grad_slots;
+        l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
+        tc2_launch(s->bwd2, l, st);
+    } else
+        k_chain<true, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
     if (between) between(user, "mlp_wgrad");
     WgradArgs w;
     w.units = s->d_units; w.work = s->d_work;
@@ -871,10 +917,30 @@ int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n
     const int64_t n_tiles = (n + NERF_TILE_M - 1) / NERF_TILE_M;
     if (n_tiles == 0 || (program != 1 && n_tiles > s->max_tiles)) return -1;
     unsigned long long *d_trace = nullptr;
-    const size_t bytes = sizeof(unsigned long long) * 3 * kTraceEvents * 2;
+    const size_t bytes = sizeof(unsigned long long) * 3 * kTraceEvents * (s->version == 2 ? 4 : 2);
     if (cudaMalloc(&d_trace, bytes) != cudaSuccess) return -2;
     cudaMemsetAsync(d_trace, 0, bytes, st);
     const DevProgram &P = program == 0 ? s->fwd_train : (program == 1 ? s->fwd_infer : s->bwd);
+    if (s->version == 2) {
+        Chain2Launch l;
+        memset(&l, 0, sizeof(l));
+        l.bwd = program == 2; l.save = program != 1;
+        l.wpack = P.wpack; l.bias = s->d_bias; l.bias_floats = (int)s->plan.bias_floats;
+        l.bias_slot = tc2_bias_upload(s, s->bias_version, s->d_bias, (int)s->plan.bias_floats, st);
+        if (l.bias_slot < 0) l.bias_slot = 0;
+        l.n_samples = n; l.S = S; l.xyz_freqs = s->g.xyz_freqs; l.dir_freqs = s->g.dir_freqs; l.num_sms = s->num_sms;
+        l.points = points; l.dirs = dirs; l.sigma = sigma_out; l.rgba = program == 2 ? const_cast<float *>(rgba) : rgba_out;
+        l.d_sigma = d_sigma; l.d_rgba = d_rgba;
+        l.save_base = program == 0 ? s->d_act : (program == 2 ? s->d_grad : nullptr);
+        l.save_slots = program == 2 ? s->plan.grad_slots : s->plan.act_slots;
+        l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
+        l.trace = d_trace;
+        tc2_launch(program == 0 ? s->fwd_train2 : (program == 1 ? s->fwd_infer2 : s->bwd2), l, st);
+        cudaMemcpyAsync(host_out, d_trace, bytes, cudaMemcpyDeviceToHost, st);
+        const cudaError_t e2 = cudaStreamSynchronize(st);
+        cudaFree(d_trace);
+        return e2 == cudaSuccess ? 0 : -2;
+    }
     ChainArgs a;
     memset(&a, 0, sizeof(a));
     a.ops = P.ops; a.jobs = P.jobs; a.n_ops = P.n_ops; a.n_jobs = P.n_jobs;

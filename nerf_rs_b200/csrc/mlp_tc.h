@@ -121,11 +121,59 @@ struct TcPlan {
     int np = 0, np2 = 0;  // hidden panels, fc9-output panels
 };
 
+// ---- v2 (mlp_tc2.cu): CTA-pair chain, two tiles ("lanes") in flight per CTA. The lane program is the v1
+// program regrouped per GEMM: one op list slice and ONE epilogue job per GEMM, plus the tile prologue (job 0).
+struct LaneOp {
+    uint32_t w_off;   // byte offset of the full chunk; CTA rank r of the pair loads rows [r n/2, (r+1) n/2)
+    uint16_t n;       // MMA N (multiple of 16)
+    uint8_t a_slot;   // lane-relative smem slot of the A operand
+    uint8_t kcount;   // K16 steps (1, 2 or 4)
+};
+struct LaneGemm {
+    uint16_t op_begin, op_end;
+};
+struct LaneJob {
+    uint8_t kind, enc;
+    uint16_t ncols;         // accumulator columns (64, 128, 256; 16 for SIGMA/RGBA)
+    uint16_t bias_off;
+    int16_t save_slot, enc_save_slot, mask_slot;
+    uint8_t out_slot, pad0;
+    uint16_t pad1;
+};
+struct LaneProgram {
+    std::vector<LaneOp> ops;
+    std::vector<LaneGemm> gemms;
+    std::vector<LaneJob> jobs;   // gemms.size() + 1
+};
+bool make_lane_program(const TcProgram &p, LaneProgram &out, std::string &err);
+struct Lane2Program;
+Lane2Program *tc2_upload(const LaneProgram &p, uint32_t bias_floats, std::string &err);
+void tc2_free(Lane2Program *d);
+struct Chain2Launch {
+    bool bwd, save;
+    const uint8_t *wpack;
+    const float *bias;
+    int32_t bias_floats, bias_slot;
+    int64_t n_samples;
+    int32_t S, xyz_freqs, dir_freqs, num_sms;
+    const float *points, *dirs;
+    float *sigma, *rgba;
+    const float *d_sigma, *d_rgba;
+    uint8_t *save_base;
+    int32_t save_slots;
+    uint32_t *mask_base;
+    int32_t mask_slots;
+    unsigned long long *trace;   // debug: [3][2048][4] clock64 stamps of CTA 0, or NULL
+};
+void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st);
+int tc2_bias_upload(const void *owner, uint64_t version, const float *d_bias, int n_floats, cudaStream_t st);
+void tc2_bias_release(const void *owner);
+
 // host-only: build all tables for a geometry. Returns false (err set) if unsupported.
 bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err);
 
 struct TcState;
-TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, std::string &err);
+TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version, std::string &err);
 void tc_destroy(TcState *s);
 size_t tc_bytes_per_tile(const TcState *s);
 void tc_pack_weights(TcState *s, const float *params, cudaStream_t st);

@@ -163,6 +163,79 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+
+// ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// all threads of every CTA in the cluster
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of another (or this) CTA of the cluster. Default semantics (release, CTA scope), as CUTLASS's
+// ClusterBarrier::arrive(cta_id) uses: the .release.cluster form costs 500-1500 cycles per arrive on B200 (measured,
+// profiles/r01_trace_notes.md). What the waiter consumes here are this CTA's OWN shared-memory panels, read by this
+// SM's tensor core through the async proxy; the writer has already executed fence.proxy.async, which completes them.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 26)) {
+            printf("nerf_b200: cluster mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc2(uint32_t smem_result_addr) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result_addr), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// CTA-pair MMA: M = 256 (128 rows from each CTA's A at the same smem offset), B = N/2 rows from each CTA,
+// D = this CTA's 128 rows x N columns at the same TMEM address in both CTAs. Issued by ONE thread of the leader.
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the mbarrier at this offset in every CTA of `cta_mask` once all MMAs issued so far by this thread completed
+__device__ __forceinline__ void umma_commit2_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     uint32_t r;

@@ -66,7 +66,10 @@ def make_ray():
 def make_model():
     torch.manual_seed(0)
     out = {}
-    for name, mcfg, r, s in (("as_shipped", M.ModelConfig.as_shipped(), 12, 16),
+    # "as_shipped" = the reference's shipped network with the INTENDED [ray, sample] transmittance layout
+    # (what the CUDA path computes); the literal graph with the .view scramble of
+    # model.rs:241 is frozen beside it as as_shipped_literal_* (oracle-only).
+    for name, mcfg, r, s in (("as_shipped", M.replace(M.ModelConfig.as_shipped(), bug_compat_T_view=False), 12, 16),
                              ("ns64", M.ModelConfig(hidden=64), 8, 16)):
         params = M.init_params(mcfg, 7)
         rng = np.random.default_rng(11)
@@ -85,6 +88,11 @@ def make_model():
                     f"{name}_gold": gold, f"{name}_pixels": pix.detach().numpy(), f"{name}_sigma": sig.detach().numpy(),
                     f"{name}_loss": np.float32(loss), f"{name}_grads": tr.grads_flat().numpy(),
                     f"{name}_params_after": tr.params_flat().numpy(), f"{name}_rs": np.array([r, s])})
+    lit = M.ModelConfig.as_shipped()
+    tr = M.Trainer(lit, M.unflatten_params(lit, torch.from_numpy(out["as_shipped_params"])), lr=5e-4)
+    pix, _ = tr.predict(torch.from_numpy(out["as_shipped_points"]), torch.from_numpy(out["as_shipped_t"]), 12, 16, None, literal=True)
+    out["as_shipped_literal_pixels"] = pix.detach().numpy()
+    out["as_shipped_literal_loss"] = np.float32(tr.step(pix, torch.from_numpy(out["as_shipped_gold"])))
     # compositing alone (model.rs:234-249) with explicit deltas
     rng = np.random.default_rng(3)
     sg = rng.random((6, 16)).astype(np.float32) * 4
