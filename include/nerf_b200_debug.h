@@ -22,6 +22,12 @@ extern "C" {
 int nerf_debug_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *jobs, int32_t *n_jobs,
                     void *chunks, int32_t *n_chunks, void *units, int32_t *n_units, int32_t *info);
 
+/* The same programs regrouped per GEMM for the CTA-pair kernel (mlp_tc2.cu): ops {u32 w_off; u16 n; u8 a_slot; u8 kcount},
+ * gemms {u16 op_begin, op_end}, jobs {u8 kind, enc; u16 ncols, bias_off; i16 save_slot, enc_save_slot, mask_slot;
+ * u8 out_slot, pad; u16 pad} (job 0 = tile prologue, job g+1 = epilogue of GEMM g). Capacities in, counts out. */
+int nerf_debug_lane_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *gemms, int32_t *n_gemms,
+                         void *jobs, int32_t *n_jobs);
+
 /* Padded-bias gather table: records of {uint32 dst_off; int64 src_base; int32 count, padded}. */
 int nerf_debug_plan_biases(const nerf_config *cfg, void *out, int32_t *n);
 

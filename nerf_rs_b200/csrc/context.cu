@@ -1003,6 +1003,28 @@ int nerf_debug_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t 
     return NERF_OK;
 }
 
+int nerf_debug_lane_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *gemms, int32_t *n_gemms, void *jobs,
+                         int32_t *n_jobs) {
+    if (!cfg || !n_ops || !n_gemms || !n_jobs) return NERF_ERR_INVALID_ARG;
+    NetGeom g;
+    build_geom(*cfg, g);
+    TcPlan plan;
+    std::string err;
+    if (!tc_build_plan(g, plan, err)) return NERF_ERR_UNSUPPORTED;
+    LaneProgram lp;
+    if (!make_lane_program(program == 0 ? plan.fwd_train : (program == 1 ? plan.fwd_infer : plan.bwd), lp, err)) {
+        fprintf(stderr, "nerf_debug_lane_plan: %s\n", err.c_str());
+        return NERF_ERR_UNSUPPORTED;
+    }
+    if (ops && *n_ops >= (int)lp.ops.size()) memcpy(ops, lp.ops.data(), lp.ops.size() * sizeof(LaneOp));
+    if (gemms && *n_gemms >= (int)lp.gemms.size()) memcpy(gemms, lp.gemms.data(), lp.gemms.size() * sizeof(LaneGemm));
+    if (jobs && *n_jobs >= (int)lp.jobs.size()) memcpy(jobs, lp.jobs.data(), lp.jobs.size() * sizeof(LaneJob));
+    *n_ops = (int)lp.ops.size();
+    *n_gemms = (int)lp.gemms.size();
+    *n_jobs = (int)lp.jobs.size();
+    return NERF_OK;
+}
+
 int nerf_debug_plan_biases(const nerf_config *cfg, void *out, int32_t *n) {
     if (!cfg || !n) return NERF_ERR_INVALID_ARG;
     NetGeom g;

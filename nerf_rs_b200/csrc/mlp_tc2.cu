@@ -254,7 +254,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             __trap();
         }
         for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(bar(kBarFullL + s), 1);
+            // leader: own half (expect_tx arrive) + the peer's relay; peer: own half only
+            ptx::mbar_init(bar(kBarFullL + s), rank == 0 ? 2 : 1);
             ptx::mbar_init(bar(kBarFullP + s), 1);
             ptx::mbar_init(bar(kBarEmpty + s), 1);
         }
@@ -298,7 +299,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                         }
                     } else {
                         ptx::mbar_wait(bar(kBarFullL + stage), phase);
-                        if (lane_id == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar(kBarFullP + stage), 0));
+                        if (lane_id == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar(kBarFullL + stage), 0));
                     }
                     __syncwarp();
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -328,8 +329,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     const LaneOp op = s_ops[i];
                     if (i != gm.op_begin && a.trace) tm0 = clock64();
                     if (!reuse) {
-                        ptx::mbar_wait(bar(kBarFullL + stage), phase);
-                        ptx::mbar_wait(bar(kBarFullP + stage), phase);
+                        ptx::mbar_wait(bar(kBarFullL + stage), phase);   // both halves: own bytes + the peer's relay
                     }
                     ptx::tc_fence_after();
                     const unsigned long long tm1 = a.trace ? clock64() : 0;

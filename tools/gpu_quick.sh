@@ -8,3 +8,4 @@ for l in open('gpurun_out/bench_quick.log'):
     if l.startswith('{'):
         d=json.loads(l); print('rays/s', round(d['value']), 'ms/step', round(d['ms_per_step'],4), 'e2e', round(d['e2e']['value']), d['roofline']['kernel_ms'], 'render', d['render'])
 PY
+[ -n "$PROBE" ] && timeout 120 python tools/hbm_probe.py

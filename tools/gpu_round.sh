@@ -9,6 +9,6 @@ if [ "$1" == "ncu" ]; then
   timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_short.log 2>&1 &&
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_list.log 2>&1
   echo "ncu list exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_chain|k_wgrad" -s 9 -c 3 -o gpurun_out/prof_mlp python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_chain|k_wgrad" -s 12 -c 4 -o gpurun_out/prof_mlp python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_full.log 2>&1
   echo "ncu full exit $?"
 fi
