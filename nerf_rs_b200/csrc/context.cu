@@ -115,6 +115,8 @@ struct nerf_ctx {
     int32_t *h_i32 = nullptr;  // pinned staging for index conversion
     size_t h_i32_cap = 0;
     bool batch_valid = false, predicted = false, acts_valid = false;
+    bool points_valid = false;            // d_points holds the batch's sample positions (else: fused sampling in the MLP prologue)
+    const ViewPose *batch_poses = nullptr;  // pose table the resident batch's ray records index
 
     // engines
     TcState *tc = nullptr;
@@ -271,8 +273,9 @@ int mlp_forward(nerf_ctx *c, int r0, int nr, int train) {
         int rc = ensure_packed(c);
         if (rc) return rc;
         Scope s(c, train ? "mlp_fwd_train" : "mlp_fwd");
-        if (tc_forward(c->tc, c->d_points + 3 * s0, c->d_dirs + 3 * (int64_t)r0, n, c->S, train, c->d_sigma + s0,
-                       c->d_rgba + 4 * s0, c->stream))
+        const TcRayInputs fused{c->d_rays + r0, c->d_t + s0, c->batch_poses};
+        if (tc_forward(c->tc, c->points_valid ? c->d_points + 3 * s0 : nullptr, c->d_dirs + 3 * (int64_t)r0, n, c->S, train,
+                       c->d_sigma + s0, c->d_rgba + 4 * s0, c->stream, &fused))
             return fail(c, NERF_ERR_INVALID_ARG, tc_last_error(c->tc));
     } else {
         Scope s(c, "mlp_fwd_simt", 12);
@@ -408,7 +411,11 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
 }
 
 int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick, const ViewPose *poses, int fixed_view,
-                const float *jitter, int randomize, uint64_t seed, int64_t ray_base, bool gather_gold) {
+                const float *jitter, int randomize, uint64_t seed, int64_t ray_base, bool gather_gold, bool write_points) {
+    // the CTA-pair MLP kernel regenerates sample positions in its prologue: points only go to HBM when somebody reads them
+    if (!(c->tc && tc_version(c->tc) == 2)) write_points = true;
+    c->points_valid = write_points;
+    c->batch_poses = poses;
     SampleArgs a;
     memset(&a, 0, sizeof(a));
     a.pix_yx = c->d_pix;
@@ -430,7 +437,7 @@ int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick
     a.rays = c->d_rays;
     a.dirs = c->d_dirs;
     a.t = c->d_t;
-    a.points = c->d_points;
+    a.points = write_points ? c->d_points : nullptr;
     a.gold = c->d_gold;
     Scope s(c, "sample");
     launch_sample(a, c->num_sms, c->stream);
@@ -734,7 +741,8 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
         dj = c->d_jitter;
     }
     const int64_t ray_base = (int64_t)c->comm.rank * R;
-    rc = run_sampler(c, R, c->d_view_pick, R / n_picks, c->d_poses, 0, dj, randomize, seed, ray_base, c->d_images != nullptr);
+    rc = run_sampler(c, R, c->d_view_pick, R / n_picks, c->d_poses, 0, dj, randomize, seed, ray_base, c->d_images != nullptr,
+                     out_points != nullptr);
     if (rc) return rc;
     c->batch_valid = true;
     c->predicted = false;
@@ -772,6 +780,7 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
     CU(c, cudaMemcpyAsync(c->d_points, query_points, sizeof(float) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->stream));
     if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->stream));
+    c->points_valid = true;
     c->batch_valid = true;
     c->predicted = false;
     return do_predict(c, train, out_rgba, out_sigma);
@@ -878,7 +887,7 @@ int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int
                 cudaStreamSynchronize(c->stream);
             }
         }
-        rc = run_sampler(c, nr, nullptr, 1, c->d_render_pose, 0, nullptr, randomize, seed, p0, false);
+        rc = run_sampler(c, nr, nullptr, 1, c->d_render_pose, 0, nullptr, randomize, seed, p0, false, false);
         if (rc) break;
         c->R = nr;  // temporarily narrow the batch view for the engines
         for (int r0 = 0; r0 < nr && rc == NERF_OK; r0 += c->chunk) {

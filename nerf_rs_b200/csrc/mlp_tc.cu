@@ -772,8 +772,10 @@ void tc_pack_weights(TcState *s, const float *params, cudaStream_t st) {
     ++s->bias_version;
 }
 
+int tc_version(const TcState *s) { return s->version; }
+
 int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, int S, int train, float *sigma, float *rgba,
-               cudaStream_t st) {
+               cudaStream_t st, const TcRayInputs *fused) {
     const int64_t n_tiles = (n + NERF_TILE_M - 1) / NERF_TILE_M;
     if (n_tiles == 0) return 0;
     if (train && n_tiles > s->max_tiles) { s->err = "tc_forward: batch exceeds the saved-activation capacity"; return -1; }
@@ -787,6 +789,10 @@ int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, in
         if (l.bias_slot < 0) { s->err = "tc_forward: bias table exceeds the constant-bank slot"; return -1; }
         l.n_samples = n; l.S = S; l.xyz_freqs = s->g.xyz_freqs; l.dir_freqs = s->g.dir_freqs; l.num_sms = s->num_sms;
         l.points = points; l.dirs = dirs; l.sigma = sigma; l.rgba = rgba;
+        if (!points) {
+            if (!fused) { s->err = "tc_forward: neither points nor ray inputs"; return -1; }
+            l.rays = fused->rays; l.t = fused->t; l.poses = fused->poses;
+        }
         l.save_base = train ? s->d_act : nullptr; l.save_slots = s->plan.act_slots;
         l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
         tc2_launch(train ? s->fwd_train2 : s->fwd_infer2, l, st);

@@ -157,6 +157,9 @@ struct Chain2Launch {
     int64_t n_samples;
     int32_t S, xyz_freqs, dir_freqs, num_sms;
     const float *points, *dirs;
+    const RayRec *rays;          // fused sampling inputs, used when points == NULL
+    const float *t;
+    const ViewPose *poses;
     float *sigma, *rgba;
     const float *d_sigma, *d_rgba;
     uint8_t *save_base;
@@ -178,8 +181,16 @@ void tc_destroy(TcState *s);
 size_t tc_bytes_per_tile(const TcState *s);
 void tc_pack_weights(TcState *s, const float *params, cudaStream_t st);
 // points [n][3], dirs [rays][3]; n samples, S samples per ray. train -> save activations.
+// Fused-sampling inputs for the CTA-pair kernel: with points == NULL the prologue rebuilds each sample position from
+// its ray record, depth and view pose (bit-identical to the standalone sampler).
+struct TcRayInputs {
+    const RayRec *rays;
+    const float *t;
+    const ViewPose *poses;
+};
 int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, int S, int train, float *sigma, float *rgba,
-               cudaStream_t st);
+               cudaStream_t st, const TcRayInputs *fused = nullptr);
+int tc_version(const TcState *s);
 // dgrad chain + weight/bias gradients accumulated (+=) into grads
 int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float *d_rgba, int64_t n, float *grads,
                 cudaStream_t st, void (*between)(void *, const char *), void *user);

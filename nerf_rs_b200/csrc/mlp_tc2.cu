@@ -22,6 +22,7 @@
 #include "kernels.h"
 #include "mlp_tc.h"
 #include "ptx.cuh"
+#include "raygeom.cuh"
 
 namespace {
 
@@ -70,7 +71,10 @@ struct Chain2Args {
     int64_t n_samples;
     int32_t n_pairs, S;       // 256-sample pair tiles
     int32_t xyz_freqs, dir_freqs;
-    const float *points;
+    const float *points;      // [n][3] sample positions, or NULL: generate them in the prologue from (rays, t, poses)
+    const RayRec *rays;       // [n / S] camera-frame ray directions + view ids (sampler output)
+    const float *t;           // [n] sorted depths
+    const ViewPose *poses;
     const float *dirs;
     float *sigma;
     float *rgba;
@@ -125,39 +129,41 @@ __device__ __forceinline__ uint32_t panel_chunk_addr(uint32_t slot_addr, uint32_
     return slot_addr + row * 128u + (((chunk ^ row) & 7u) << 4);
 }
 
-// [v, sin(2^k v), cos(2^k v)]_k of a 3-vector, zero padded to 64; this warp stores 16-byte chunks [kCh0, kCh1).
-// Base sin/cos are accurate (sincosf); octaves use the double-angle recurrence (error far below bf16 resolution).
-template <int kMaxF>
-__device__ __forceinline__ void encode_panel(uint32_t slot_addr, uint32_t row, const float v[3], int freqs, int ch0, int ch1) {
-    float f[64];
+// Positional encoding [v, sin(2^k v), cos(2^k v)]_k of a 3-vector, zero padded to 64 features, written as the bf16
+// 16-byte chunks [kCh0, kCh1) of a panel row (each column-slice warp writes its own chunks). Every feature is evaluated
+// independently with the SFU (sin.approx / cos.approx of the exactly scaled argument 2^k v): at |2^k v| <= ~1.5e3 the
+// absolute error is ~1e-4, an order of magnitude below the bf16 rounding the value gets next, and there is no serial
+// dependency. (An accurate sincosf + double-angle recurrence, inlined at three call sites, made the kernel 155 KB of
+// SASS and cost 1-5 k cycles per tile on the critical path; a compact run-time-indexed loop was no better.)
+template <int kCh0, int kCh1>
+__device__ __forceinline__ void encode_chunks(uint32_t slot_addr, uint32_t row, float v0, float v1, float v2, int freqs) {
+    const int n_feat = 3 + 6 * freqs;
 #pragma unroll
-    for (int i = 0; i < 64; ++i) f[i] = 0.f;
-    f[0] = v[0]; f[1] = v[1]; f[2] = v[2];
-    float s[3], c[3];
+    for (int ch = kCh0; ch < kCh1; ++ch) {
+        float f[8];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) sincosf(v[d], &s[d], &c[d]);
-#pragma unroll
-    for (int k = 0; k < kMaxF; ++k) {
-        if (k < freqs) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                f[3 + 6 * k + d] = s[d];
-                f[3 + 6 * k + 3 + d] = c[d];
-                const float s2 = 2.f * s[d] * c[d];
-                const float c2 = fmaf(-2.f * s[d], s[d], 1.f);
-                s[d] = s2;
-                c[d] = c2;
-            }
+        for (int e = 0; e < 8; ++e) {
+            const int fi = 8 * ch + e;                                 // compile-time after unrolling
+            const int g = fi - 3;
+            const int k = g / 6, r = g - 6 * k;                        // octave, slot within the octave (sin xyz | cos xyz)
+            const int d = fi < 3 ? fi : (r < 3 ? r : r - 3);
+            const float x = d == 0 ? v0 : (d == 1 ? v1 : v2);
+            const float arg = x * (float)(1 << (fi < 3 ? 0 : k));      // x * 2^k, exact
+            const float val = fi < 3 ? x : (r < 3 ? __sinf(arg) : __cosf(arg));
+            f[e] = fi < n_feat ? val : 0.f;
         }
+        st_shared_v4(panel_chunk_addr(slot_addr, row, (uint32_t)ch), ptx::pack_bf16x2(f[0], f[1]), ptx::pack_bf16x2(f[2], f[3]),
+                     ptx::pack_bf16x2(f[4], f[5]), ptx::pack_bf16x2(f[6], f[7]));
     }
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        if (ch >= ch0 && ch < ch1) {   // warp-uniform
-            uint32_t w[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) w[e] = ptx::pack_bf16x2(f[8 * ch + 2 * e], f[8 * ch + 2 * e + 1]);
-            st_shared_v4(panel_chunk_addr(slot_addr, row, ch), w[0], w[1], w[2], w[3]);
-        }
+}
+// column slice h of kSplit writes chunks [h * 8/kSplit, (h+1) * 8/kSplit) of the row
+__device__ __forceinline__ void encode_row(int h, uint32_t slot_addr, uint32_t row, float v0, float v1, float v2, int freqs) {
+    static_assert(kSplit == 4, "column split");
+    switch (h) {
+        case 0: encode_chunks<0, 2>(slot_addr, row, v0, v1, v2, freqs); break;
+        case 1: encode_chunks<2, 4>(slot_addr, row, v0, v1, v2, freqs); break;
+        case 2: encode_chunks<4, 6>(slot_addr, row, v0, v1, v2, freqs); break;
+        default: encode_chunks<6, 8>(slot_addr, row, v0, v1, v2, freqs); break;
     }
 }
 // panel whose only non-zero entries are the first four bf16 of each row; this warp writes chunks [ch0, ch1)
@@ -373,18 +379,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         auto write_enc = [&](uint8_t kind, uint8_t enc, uint32_t e_addr, int64_t gs, bool valid) {
             if (kind == EK_PROLOGUE_FWD || enc == ENC_X) {
                 float v[3] = {0.f, 0.f, 0.f};
-                if (valid) { v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2]; }
-                encode_panel<10>(e_addr, row, v, a.xyz_freqs, ech0, ech1);
-            } else if (enc == ENC_D) {
-                if (ech0 < 4) {   // 3 + 6*4 = 27 values: chunks 0..3; the rest of the row is zero
-                    float v[3] = {0.f, 0.f, 0.f};
-                    if (valid) {
-                        const int64_t ray = gs / a.S;
-                        v[0] = a.dirs[3 * ray]; v[1] = a.dirs[3 * ray + 1]; v[2] = a.dirs[3 * ray + 2];
+                if (valid) {
+                    if (a.points) {
+                        v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2];
+                    } else {
+                        // fused sampling: the point never exists in HBM -- same ops as k_sample, bit for bit
+                        const RayRec rec = a.rays[gs / a.S];
+                        raygeom::sample_point(a.poses[rec.view], rec.to, a.t[gs], v);
                     }
-                    encode_panel<4>(e_addr, row, v, a.dir_freqs, ech0, ech1 < 4 ? ech1 : 4);
                 }
-                if (ech1 > 4) write_sparse_panel(e_addr, row, ech0 > 4 ? ech0 : 4, ech1, 0u, 0u);
+                encode_row(h, e_addr, row, v[0], v[1], v[2], a.xyz_freqs);
+            } else if (enc == ENC_D) {
+                float v[3] = {0.f, 0.f, 0.f};   // 3 + 6*4 = 27 values; features beyond 3 + 6*freqs are written as zeros
+                if (valid && ech0 < 4) {
+                    const int64_t ray = gs / a.S;
+                    v[0] = a.dirs[3 * ray]; v[1] = a.dirs[3 * ray + 1]; v[2] = a.dirs[3 * ray + 2];
+                }
+                encode_row(h, e_addr, row, v[0], v[1], v[2], a.dir_freqs);
             } else if (enc == ENC_DSIGMA) {
                 const float ds = valid ? a.d_sigma[gs] : 0.f;
                 write_sparse_panel(e_addr, row, ech0, ech1, ptx::pack_bf16x2(ds, 0.f), 0u);
@@ -670,7 +681,7 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
     a.n_pairs = (int)((n_tiles + 1) / 2);
     a.S = l.S;
     a.xyz_freqs = l.xyz_freqs; a.dir_freqs = l.dir_freqs;
-    a.points = l.points; a.dirs = l.dirs; a.sigma = l.sigma; a.rgba = l.rgba; a.d_sigma = l.d_sigma; a.d_rgba = l.d_rgba;
+    a.points = l.points; a.rays = l.rays; a.t = l.t; a.poses = l.poses; a.dirs = l.dirs; a.sigma = l.sigma; a.rgba = l.rgba; a.d_sigma = l.d_sigma; a.d_rgba = l.d_rgba;
     a.save_base = l.save_base; a.save_slots = l.save_slots; a.mask_base = l.mask_base; a.mask_slots = l.mask_slots;
     a.trace = l.trace;
     const int max_clusters = l.num_sms / 2;

@@ -7,12 +7,14 @@
 // matrices and tan(FOV/2)*HITHER come from the host.
 #include "common.cuh"
 #include "kernels.h"
+#include "raygeom.cuh"
 
 namespace {
 
-__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+using raygeom::add;
+using raygeom::mul;
+using raygeom::rotate_yaw_pitch;
+using raygeom::sub;
 
 // screen_to_world (ray_sampling.rs:79-93), op for op. view=(0,0,1), left=(-1,0,0), UP=(0,1,0)
 // are the normalised constants the reference recomputes per call.
@@ -30,18 +32,6 @@ __device__ __forceinline__ void screen_to_world(float x, float y, float width, f
     to[0] = mul(sx, inv);
     to[1] = mul(sy, inv);
     to[2] = mul(sz, inv);
-}
-
-__device__ __forceinline__ void rotate_yaw_pitch(const ViewPose &vp, const float v[3], float out[3]) {
-    // rotateYaw: row_mat3x4_transform_pos3 (ray_sampling.rs:20-26)
-    float y3[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-        y3[i] = add(add(add(mul(vp.yaw[i][0], v[0]), mul(vp.yaw[i][1], v[1])), mul(vp.yaw[i][2], v[2])), vp.yaw[i][3]);
-        // rotatePitch: col_mat3_transform (ray_sampling.rs:68)
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-        out[i] = add(add(mul(vp.pitch[0][i], y3[0]), mul(vp.pitch[1][i], y3[1])), mul(vp.pitch[2][i], y3[2]));
 }
 
 // Philox picks for pixel rows/cols and views (replaces Tensor::randint, dataset.rs:12,19,88).
@@ -131,9 +121,8 @@ k_sample(SampleArgs a) {
             if (i < S) {
                 const float t = st[i];
                 a.t[(size_t)r * S + i] = t;
-                float p[3] = {add(0.f, mul(to[0], t)), add(0.f, mul(to[1], t)), add(-1.f, mul(to[2], t))};
                 float q[3];
-                rotate_yaw_pitch(vp, p, q);
+                raygeom::sample_point(vp, to, t, q);
                 s_p[warp][3 * lane] = q[0]; s_p[warp][3 * lane + 1] = q[1]; s_p[warp][3 * lane + 2] = q[2];
             }
             __syncwarp();

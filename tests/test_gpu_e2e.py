@@ -95,3 +95,26 @@ def test_checkpoint_round_trip():
         out, _ = mm.predict(pts, t, dirs.reshape(-1), train=True)
         nb.Trainer(mm).step(out, gold)
     assert np.allclose(m.get_weights(), m2.get_weights(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("s", [64, 192])
+def test_fused_sampling_in_the_mlp_prologue_is_bit_identical(s):
+    """North star: sample positions are generated inside the MLP kernel's prologue and never written to HBM.
+    The fused path must give exactly the pixels / densities of the path that reads the sampler's points."""
+    cfg = nb.default_config(image_w=100, image_h=100, num_rays=96, num_samples=s, hidden=256)
+    m = nb.NeRF(cfg)
+    mcfg = G.model_cfg(cfg)
+    m.set_weights(M.flatten_params(M.init_params(mcfg, 2)).numpy())
+    rng = np.random.default_rng(3)
+    m.set_images(rng.random((6, 100 * 100, 4)).astype(np.float32))
+    m.set_view_angles(nb.get_view_angles(6)[10:16])
+    idx = np.stack([rng.integers(0, 100, 96), rng.integers(0, 100, 96)], 1).astype(np.int64)
+    vi = rng.integers(0, 6, 6).astype(np.int64)
+    u = rng.random((96, s)).astype(np.float32)
+    b = m.get_batch(idx, vi, 6, u, True, 0, want=("points", "t", "dirs"))     # points requested -> written to HBM, MLP reads them
+    out_a, sig_a = m.predict(train=False)
+    m.get_batch(idx, vi, 6, u, True, 0, want=())                              # nothing requested -> fused: no points in HBM
+    out_b, sig_b = m.predict(train=False)
+    assert np.array_equal(sig_a, sig_b) and np.array_equal(out_a, out_b)
+    out_c, sig_c = m.predict(b["points"].reshape(-1), b["t"].reshape(-1), b["dirs"].reshape(-1), train=False)   # literal signature
+    assert np.array_equal(sig_a, sig_c) and np.array_equal(out_a, out_c)
