@@ -174,30 +174,25 @@ __device__ __forceinline__ void write_sparse_panel(uint32_t slot_addr, uint32_t 
 
 // 32 accumulator columns -> 16 packed bf16x2 words (bias + ReLU/linear, or ReLU-mask select for the backward chain)
 template <bool kSave, uint8_t kKind>
-__device__ __forceinline__ void epi_group(const uint32_t (&r)[32], const float *bias_g, uint32_t &mask, uint32_t (&w)[16]) {
+__device__ __forceinline__ void epi_group(const uint32_t (&r)[32], int bidx, uint32_t &mask, uint32_t (&w)[16]) {
     if (kKind == EK_RELU || kKind == EK_LINEAR) {
-        const float4 *bp = reinterpret_cast<const float4 *>(bias_g);
         uint32_t signs = 0;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = bp[j4];   // constant bank, warp-uniform address
-            const float v0 = __uint_as_float(r[4 * j4 + 0]) + b.x;
-            const float v1 = __uint_as_float(r[4 * j4 + 1]) + b.y;
-            const float v2 = __uint_as_float(r[4 * j4 + 2]) + b.z;
-            const float v3 = __uint_as_float(r[4 * j4 + 3]) + b.w;
+        for (int j2 = 0; j2 < 16; ++j2) {
+            // packed fp32x2 add (sm_100): one instruction and one 64-bit constant operand per column pair; the bias
+            // comes from the constant bank at a warp-uniform index
+            const float2 b = *reinterpret_cast<const float2 *>(&c_bias[bidx + 2 * j2]);
+            unsigned long long acc2, bias2, sum2;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "r"(r[2 * j2]), "r"(r[2 * j2 + 1]));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(bias2) : "f"(b.x), "f"(b.y));
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum2) : "l"(acc2), "l"(bias2));
+            float v0, v1;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(sum2));
             if (kSave && kKind == EK_RELU) {
                 signs = __funnelshift_l(__float_as_uint(v0), signs, 1);
                 signs = __funnelshift_l(__float_as_uint(v1), signs, 1);
-                signs = __funnelshift_l(__float_as_uint(v2), signs, 1);
-                signs = __funnelshift_l(__float_as_uint(v3), signs, 1);
             }
-            if (kKind == EK_RELU) {
-                w[2 * j4] = ptx::pack_bf16x2_relu(v0, v1);
-                w[2 * j4 + 1] = ptx::pack_bf16x2_relu(v2, v3);
-            } else {
-                w[2 * j4] = ptx::pack_bf16x2(v0, v1);
-                w[2 * j4 + 1] = ptx::pack_bf16x2(v2, v3);
-            }
+            w[j2] = (kKind == EK_RELU) ? ptx::pack_bf16x2_relu(v0, v1) : ptx::pack_bf16x2(v0, v1);
         }
         mask = ~signs;  // bit (31 - col) set = pre-activation sign bit clear
     } else {
@@ -222,18 +217,23 @@ __device__ __forceinline__ void store_group(uint32_t lane_base, uint32_t out_slo
 // One warp's share of a hidden-layer epilogue: 32-column groups [G0, G1) of the accumulator, one at a time
 // (with four warps per scheduler the other warps cover the TMEM-load and store latencies).
 template <bool kSave, uint8_t kKind>
-__device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uint32_t lane_base, const float *bias, uint32_t *mask_row,
+__device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uint32_t lane_base, int bias_base, uint32_t *mask_row,
                                            uint32_t row, int G0, int G1, const uint32_t (&pm)[8 / kSplit]) {
-    for (int G = G0; G < G1; ++G) {
-        uint32_t r[32];
-        uint32_t m = 0;
-        if (kKind == EK_DMASK) m = pm[(G - G0) & (8 / kSplit - 1)];   // prefetched before the accumulator wait
-        ptx::tmem_ld32(taddr + (uint32_t)G * 32u, r);
-        ptx::tmem_ld_wait();
-        uint32_t w[16];
-        epi_group<kSave, kKind>(r, bias + j.bias_off + G * 32, m, w);
-        store_group(lane_base, j.out_slot, row, G, w);
-        if (kSave && kKind == EK_RELU && mask_row) mask_row[G] = m;
+    static_assert(8 / kSplit == 2, "a column slice is at most two 32-column groups");
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {          // unrolled: G stays in the uniform datapath
+        const int G = G0 + g;
+        if (G < G1) {
+            uint32_t r[32];
+            uint32_t m = 0;
+            if (kKind == EK_DMASK) m = pm[g];   // prefetched before the accumulator wait
+            ptx::tmem_ld32(taddr + (uint32_t)G * 32u, r);
+            ptx::tmem_ld_wait();
+            uint32_t w[16];
+            epi_group<kSave, kKind>(r, bias_base + (int)j.bias_off + G * 32, m, w);
+            store_group(lane_base, j.out_slot, row, G, w);
+            if (kSave && kKind == EK_RELU && mask_row) mask_row[G] = m;
+        }
     }
 }
 
@@ -249,7 +249,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
     const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
     auto bar = [&](int id) { return bars + 8u * (uint32_t)id; };
 
-    const float *g_bias = c_bias + a.bias_slot * kBiasSlotFloats;
+    const int bias_base = a.bias_slot * kBiasSlotFloats;
+    const float *g_bias = c_bias + bias_base;
     const LaneOp *s_ops = a.ops;
     const LaneGemm *s_gemms = a.gemms;
     const LaneJob *s_jobs = a.jobs;
@@ -280,6 +281,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
+    // Register rebalancing (setmaxnreg): the four service warps (producer, MMA issuer / relay, TMEM allocator, store warp)
+    // need few registers; the 16 epilogue warps hold 32 accumulator columns, 16 packed words and addressing.
+    // The pool is what the CTA was launched with (96 x 640 registers): 128 x 40 + 512 x 104 fits, 112 would block forever.
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 || (warp == 1 && rank != 0)) {
         // ===== warp 0 (both CTAs): weight producer -- this CTA's half of every chunk, once per lane GROUP when the
         //       GEMM is shareable, once per lane otherwise
@@ -363,7 +369,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (kSave && warp == 3) {
+        // ================= store warp (training): bulk-stores every step's panels to the per-tile save area ==========
+        // Steps arrive in the epilogue's order. A lane's panels may be rewritten once its stores have finished READING
+        // shared memory (SAVE_FREE); the global writes themselves only have to land before the kernel ends.
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms);
+        uint32_t rph = 0;   // bit l: parity to wait for on SAVE_READY[l]
+        const LaneJob pj = s_jobs[0];
+        int p, nl, pr0, pr1;
+        auto store_step = [&](int ln, auto issue) {
+            ptx::mbar_wait(bar(kBarSaveReady + ln), (rph >> ln) & 1u);
+            rph ^= 1u << ln;
+            if (lane_id == 0) {
+                issue();
+                ptx::bulk_commit();
+                ptx::bulk_wait_read<0>();
+                ptx::mbar_arrive(bar(kBarSaveFree + ln));
+            }
+            __syncwarp();
+        };
+        while (sch.next(p, nl, pr0, pr1)) {
+            for (int ln = 0; ln < nl; ++ln) {
+                const int pr = ln ? pr1 : pr0;
+                const bool first_tile = pr < sch.stride;
+                const bool has_next = pr + sch.stride < a.n_pairs;
+                const uint32_t lane_base = sbase + (uint32_t)ln * kLaneBytes;
+                const uint32_t e_addr = lane_base + TC_SLOT_E * kSlotBytes;
+                uint8_t *tile_base = a.save_base + (size_t)(2 * pr + (int)rank) * a.save_slots * kSlotBytes;
+                uint8_t *next_base = a.save_base + (size_t)(2 * (pr + sch.stride) + (int)rank) * a.save_slots * kSlotBytes;
+                if (p == 0 && first_tile)
+                    store_step(ln, [&]() {
+                        if (pj.enc_save_slot >= 0) ptx::bulk_s2g(tile_base + (size_t)pj.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
+                    });
+                const LaneJob j = s_jobs[p + 1];
+                store_step(ln, [&]() {
+                    // consecutive panels are contiguous both in shared memory and in the save area: one copy
+                    if (j.save_slot >= 0)
+                        ptx::bulk_s2g(tile_base + (size_t)j.save_slot * kSlotBytes, lane_base + (uint32_t)j.out_slot * kSlotBytes,
+                                      (uint32_t)(j.ncols >> 6) * kSlotBytes);
+                    if (j.enc_save_slot >= 0) ptx::bulk_s2g(tile_base + (size_t)j.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
+                    if (p == a.n_gemms - 1 && has_next && pj.enc_save_slot >= 0)
+                        ptx::bulk_s2g(next_base + (size_t)pj.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
+                });
+            }
+        }
+        if (lane_id == 0) ptx::bulk_wait_all<0>();
+    }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= epilogue warps =================
         // warp (q, h): TMEM lane quarter q (rows 32q..32q+31), column slice h of kSplit of the accumulator
         const uint32_t we = (uint32_t)(warp - 4);
@@ -473,11 +526,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * 256u;
             if (j.kind == EK_RELU || j.kind == EK_LINEAR || j.kind == EK_DMASK || j.kind == EK_DCOPY) {
                 if (!kBwd) {
-                    if (j.kind == EK_RELU) epi_hidden<kSave, EK_RELU>(j, taddr, lane_base, g_bias, mask_row, row, G0, G1, pm);
-                    else epi_hidden<kSave, EK_LINEAR>(j, taddr, lane_base, g_bias, mask_row, row, G0, G1, pm);
+                    if (j.kind == EK_RELU) epi_hidden<kSave, EK_RELU>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
+                    else epi_hidden<kSave, EK_LINEAR>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
                 } else {
-                    if (j.kind == EK_DMASK) epi_hidden<kSave, EK_DMASK>(j, taddr, lane_base, g_bias, mask_row, row, G0, G1, pm);
-                    else epi_hidden<kSave, EK_DCOPY>(j, taddr, lane_base, g_bias, mask_row, row, G0, G1, pm);
+                    if (j.kind == EK_DMASK) epi_hidden<kSave, EK_DMASK>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
+                    else epi_hidden<kSave, EK_DCOPY>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
                 }
             } else if (j.kind == EK_SIGMA || j.kind == EK_RGBA) {
                 if (h == 0) {
@@ -514,51 +567,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             ++epi_ev;
           }
         }
-    } else if (kSave && warp == 3) {
-        // ================= store warp (training): bulk-stores every step's panels to the per-tile save area ==========
-        // Steps arrive in the epilogue's order. A lane's panels may be rewritten once its stores have finished READING
-        // shared memory (SAVE_FREE); the global writes themselves only have to land before the kernel ends.
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms);
-        uint32_t rph = 0;   // bit l: parity to wait for on SAVE_READY[l]
-        const LaneJob pj = s_jobs[0];
-        int p, nl, pr0, pr1;
-        auto store_step = [&](int ln, auto issue) {
-            ptx::mbar_wait(bar(kBarSaveReady + ln), (rph >> ln) & 1u);
-            rph ^= 1u << ln;
-            if (lane_id == 0) {
-                issue();
-                ptx::bulk_commit();
-                ptx::bulk_wait_read<0>();
-                ptx::mbar_arrive(bar(kBarSaveFree + ln));
-            }
-            __syncwarp();
-        };
-        while (sch.next(p, nl, pr0, pr1)) {
-            for (int ln = 0; ln < nl; ++ln) {
-                const int pr = ln ? pr1 : pr0;
-                const bool first_tile = pr < sch.stride;
-                const bool has_next = pr + sch.stride < a.n_pairs;
-                const uint32_t lane_base = sbase + (uint32_t)ln * kLaneBytes;
-                const uint32_t e_addr = lane_base + TC_SLOT_E * kSlotBytes;
-                uint8_t *tile_base = a.save_base + (size_t)(2 * pr + (int)rank) * a.save_slots * kSlotBytes;
-                uint8_t *next_base = a.save_base + (size_t)(2 * (pr + sch.stride) + (int)rank) * a.save_slots * kSlotBytes;
-                if (p == 0 && first_tile)
-                    store_step(ln, [&]() {
-                        if (pj.enc_save_slot >= 0) ptx::bulk_s2g(tile_base + (size_t)pj.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
-                    });
-                const LaneJob j = s_jobs[p + 1];
-                store_step(ln, [&]() {
-                    // consecutive panels are contiguous both in shared memory and in the save area: one copy
-                    if (j.save_slot >= 0)
-                        ptx::bulk_s2g(tile_base + (size_t)j.save_slot * kSlotBytes, lane_base + (uint32_t)j.out_slot * kSlotBytes,
-                                      (uint32_t)(j.ncols >> 6) * kSlotBytes);
-                    if (j.enc_save_slot >= 0) ptx::bulk_s2g(tile_base + (size_t)j.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
-                    if (p == a.n_gemms - 1 && has_next && pj.enc_save_slot >= 0)
-                        ptx::bulk_s2g(next_base + (size_t)pj.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
-                });
-            }
-        }
-        if (lane_id == 0) ptx::bulk_wait_all<0>();
     }
 
     ptx::tc_fence_before();

@@ -1,8 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 8 gpurun_out/pytest_gpu.log
-timeout 300 python tools/trace_chain2.py > gpurun_out/trace2.log 2>&1; echo "trace exit $?"; grep -n "===\|epilogue span\|MMA thread\|producer\|D-encode" gpurun_out/trace2.log
-for i in 1 2; do timeout 300 python bench.py --steps 200 --warmup 5 --no-cpu 2>/dev/null | python -c "
+timeout 120 python -m pytest tests/test_golden.py -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "golden exit $rc"; tail -n 4 gpurun_out/pytest_gpu.log
+[ $rc -ne 0 ] && exit 1
+timeout 600 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 6 gpurun_out/pytest_gpu.log
+timeout 200 python tools/trace_chain2.py > gpurun_out/trace2.log 2>&1; echo "trace exit $?"; grep -n "===\|epilogue span\|MMA thread\|producer\|D-encode" gpurun_out/trace2.log
+for i in 1 2; do timeout 200 python bench.py --steps 200 --warmup 5 --no-cpu 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
