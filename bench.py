@@ -260,7 +260,7 @@ def main():
                      "kernels": per_kernel,
                      "kernel_ms": {k: round(v["ms"], 4) for k, v in kern.items()}})
 
-    # ---- inference / render throughput (forward only, no saved activations)
+    # ---- inference: MLP forward alone at the training batch shape (no saved activations)
     model.profile(True)
     for it in range(5):
         model.get_batch(None, None, 64, None, True, 9000 + it, want=())
@@ -270,11 +270,35 @@ def main():
     render = None
     if "mlp_fwd" in pr and pr["mlp_fwd"][0] > 0:
         fwd_ms = pr["mlp_fwd"][0] / pr["mlp_fwd"][1]
-        tot = sum(v[0] for v in pr.values()) / 5
-        render = {"msamples_per_sec": nsamp / (tot * 1e-3) / 1e6, "mlp_fwd_ms": fwd_ms,
-                  "mlp_fwd_tflops": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12,
+        render = {"mlp_fwd_ms": fwd_ms, "mlp_fwd_tflops": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12,
                   "mlp_fwd_frac_of_sustained_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_sus,
                   "mlp_fwd_frac_of_burst_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_burst}
+        # ---- novel-view render (BASELINE configs[3]): full 800x800 frame x 192 samples, rows sharded over the ranks,
+        #      one all-gather; the packed 0x00RRGGBB frame comes back to the host inside the timed region
+        rs = 192
+        rcfg = nb.default_config(image_w=IMG, image_h=IMG, num_rays=16384, num_samples=rs, hidden=W)
+        rmodel = nb.NeRF(rcfg, device=local)
+        rmodel.set_weights(model.get_weights())
+        if world > 1:
+            uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid2.copy_(torch.frombuffer(bytearray(nb.NeRF.comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid2, 0)
+            rmodel.comm_init_rank(bytes(uid2.cpu().numpy().tobytes()), rank, world)
+        rmodel.render_sharded(0.3, 0.2, randomize=True, seed=1, packed=True)          # warm-up frame
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_frames = 2
+        for f in range(n_frames):
+            rmodel.render_sharded(0.3 + 0.1 * f, 0.2, randomize=True, seed=2 + f, packed=True)
+        tt_frames = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt_frames, op=dist.ReduceOp.MAX)
+        frame_s = float(tt_frames.item()) / n_frames
+        render.update({"workload": f"{IMG}x{IMG} frame x {rs} samples, rows sharded over {world} GPU(s), all-gather + D2H of rgba and 0RGB",
+                       "frame_ms": frame_s * 1e3, "msamples_per_sec": IMG * IMG * rs / frame_s / 1e6})
+        rmodel.close()
 
     # ---- end to end through the reference-facing calls with host buffers
     from tests import gpu_util as G

@@ -78,6 +78,8 @@ pub mod sys {
         pub fn nerf_sync(ctx: *mut nerf_ctx) -> c_int;
         pub fn nerf_render(ctx: *mut nerf_ctx, yaw: f32, pitch: f32, y0: i32, y1: i32, randomize: i32, seed: u64,
                            out_rgba: *mut f32, out_0rgb: *mut u32) -> c_int;
+        pub fn nerf_render_sharded(ctx: *mut nerf_ctx, yaw: f32, pitch: f32, randomize: i32, seed: u64,
+                                   out_rgba: *mut f32, out_0rgb: *mut u32) -> c_int;
         pub fn nerf_comm_unique_id(id128: *mut c_void) -> c_int;
         pub fn nerf_comm_init_rank(ctx: *mut nerf_ctx, id128: *const c_void, rank: i32, nranks: i32) -> c_int;
         pub fn nerf_comm_destroy(ctx: *mut nerf_ctx) -> c_int;

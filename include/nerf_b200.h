@@ -159,6 +159,12 @@ int nerf_sync(nerf_ctx *ctx);
 int nerf_render(nerf_ctx *ctx, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed,
                 float *out_rgba, uint32_t *out_0rgb);
 
+/* The same frame sharded over the ranks of nerf_comm_init_rank: rank r renders the row band [r H/N, (r+1) H/N) (H % N
+ * must be 0), then ONE NCCL all-gather assembles the frame on every rank -- the only collective of the render path.
+ * out_rgba [H*W*4] / out_0rgb [H*W] receive the FULL frame (either may be NULL). Without a communicator: one band = all. */
+int nerf_render_sharded(nerf_ctx *ctx, float yaw, float pitch, int32_t randomize, uint64_t seed, float *out_rgba,
+                        uint32_t *out_0rgb);
+
 /* ---- data-parallel training (no reference counterpart: it is single device) --------
  * One process per GPU. Rank 0 calls nerf_comm_unique_id, the host distributes the 128
  * bytes, every rank calls nerf_comm_init_rank. After that nerf_step all-reduces the

@@ -67,6 +67,7 @@ SIGNATURES = {
     "nerf_last_loss": (ctypes.c_int, [vp, P(f32)]),
     "nerf_sync": (ctypes.c_int, [vp]),
     "nerf_render": (ctypes.c_int, [vp, f32, f32, i32, i32, i32, u64, vp, vp]),
+    "nerf_render_sharded": (ctypes.c_int, [vp, f32, f32, i32, u64, vp, vp]),
     "nerf_comm_unique_id": (ctypes.c_int, [vp]),
     "nerf_comm_init_rank": (ctypes.c_int, [vp, vp, i32, i32]),
     "nerf_comm_destroy": (ctypes.c_int, [vp]),

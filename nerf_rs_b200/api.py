@@ -207,6 +207,14 @@ class NeRF:
         _check(self.h, self.lib.nerf_render(self.h, yaw, pitch, y0, y1, 1 if randomize else 0, seed, _ptr(rgba), _ptr(pk)))
         return (rgba, pk) if packed else rgba
 
+    def render_sharded(self, yaw, pitch, randomize=False, seed=0, packed=False):
+        """Full frame with the rows sharded over the data-parallel ranks (comm_init_rank); one all-gather at the end."""
+        w, h = self.cfg.image_w, self.cfg.image_h
+        rgba = np.empty((h, w, 4), dtype=np.float32)
+        pk = np.empty((h, w), dtype=np.uint32) if packed else None
+        _check(self.h, self.lib.nerf_render_sharded(self.h, yaw, pitch, 1 if randomize else 0, seed, _ptr(rgba), _ptr(pk)))
+        return (rgba, pk) if packed else rgba
+
     def train_iter(self, seed):
         _check(self.h, self.lib.nerf_train_iter(self.h, seed))
 

@@ -147,6 +147,29 @@ k_composite(CompositeArgs a) {
             }
         }
     }
+    // ---- fused loss: the last block to finish sums the per-ray squared errors in a fixed order (deterministic)
+    if (kBackward && a.loss_out) {
+        __shared__ float sh[kWarps * 32];
+        __shared__ bool is_last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) is_last = atomicAdd(a.done_counter, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (is_last) {
+            float s = 0.f;
+            for (int i = threadIdx.x; i < a.num_rays; i += blockDim.x) s += __ldcg(a.ray_loss + i);
+            sh[threadIdx.x] = s;
+            __syncthreads();
+            for (int d = (kWarps * 32) >> 1; d > 0; d >>= 1) {
+                if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                *a.loss_out = sh[0] * a.loss_scale;
+                *a.done_counter = 0u;
+            }
+        }
+    }
 }
 
 // deterministic fixed-order reduction of per-ray squared errors -> mean loss

@@ -115,6 +115,7 @@ struct nerf_ctx {
     int32_t *h_i32 = nullptr;  // pinned staging for index conversion
     size_t h_i32_cap = 0;
     bool batch_valid = false, predicted = false, acts_valid = false;
+    int gen_pix = 0, gen_view = 0, pick_views = 0;   // Philox picks requested for the next sampler launch
     bool points_valid = false;            // d_points holds the batch's sample positions (else: fused sampling in the MLP prologue)
     const ViewPose *batch_poses = nullptr;  // pose table the resident batch's ray records index
 
@@ -130,6 +131,8 @@ struct nerf_ctx {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     uint8_t *d_flush = nullptr;
     size_t flush_bytes = 0;
+    float *d_frame_rgba = nullptr;       // full-frame render targets (lazily allocated)
+    uint32_t *d_frame_0rgb = nullptr;
 };
 
 namespace {
@@ -258,7 +261,7 @@ void prof_between(void *user, const char *name) {
 
 int ensure_packed(nerf_ctx *c) {
     if (c->weights_dirty && c->tc) {
-        Scope s(c, "pack_weights", 3);
+        Scope s(c, "pack_weights", 1);
         tc_pack_weights(c->tc, c->d_params, c->stream);
     }
     c->weights_dirty = false;
@@ -316,7 +319,7 @@ int composite_forward(nerf_ctx *c, int nr, float *out) {
     return check_launch(c, "composite_fwd");
 }
 
-int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma) {
+int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool skip_composite = false) {
     if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "predict: no batch (call nerf_get_batch or nerf_predict_points)");
     c->acts_valid = false;
     for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
@@ -326,7 +329,8 @@ int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma) {
         if (rc) return rc;
         if (keep) c->acts_valid = true;
     }
-    int rc = composite_forward(c, c->R, c->d_out);
+    // (a fused training iteration gets its pixels from the compositing backward kernel, which recomputes them)
+    int rc = skip_composite ? NERF_OK : composite_forward(c, c->R, c->d_out);
     if (rc) return rc;
     c->predicted = true;
     if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_out, sizeof(float) * 4 * c->R, cudaMemcpyDeviceToHost, c->stream));
@@ -356,12 +360,12 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         a.ray_loss = c->d_ray_loss;
         a.d_sigma = c->d_dsigma;
         a.d_colors = c->d_drgba;
+        a.out = c->d_out;                              // the backward pass recomputes the pixels on its way
+        a.loss_out = c->d_loss;                        // ... and the mean loss (model.rs:298), reduced by its last block
+        a.loss_scale = 1.f / (4.f * (float)c->R);
+        a.done_counter = reinterpret_cast<unsigned int *>(c->d_loss + 2);
         Scope s(c, "composite_bwd");
         launch_composite_bwd(a, c->num_sms, c->stream);
-    }
-    {
-        Scope s(c, "loss_reduce");
-        launch_loss_reduce(c->d_ray_loss, c->R, 1.f / (4.f * (float)c->R), c->d_loss, c->stream);
     }
     int rc = check_launch(c, "composite_bwd");
     if (rc) return rc;
@@ -422,6 +426,11 @@ int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick
     a.view_pick = view_pick;
     a.rays_per_pick = rays_per_pick;
     a.fixed_view = fixed_view;
+    a.gen_pix = view_pick ? c->gen_pix : 0;        // (render passes explicit pixels and a fixed view)
+    a.gen_view = view_pick ? c->gen_view : 0;
+    a.n_views = c->pick_views;
+    a.pix_out = c->d_pix;
+    a.view_out = c->d_view_pick;
     a.poses = poses;
     a.jitter = jitter;
     a.images = gather_gold ? c->d_images : nullptr;
@@ -501,7 +510,7 @@ int nerf_destroy(nerf_ctx *c) {
     void *ptrs[] = {c->d_params, c->d_grads, c->d_m, c->d_v, c->d_images, c->d_poses, c->d_render_pose, c->d_pix, c->d_view_pick,
                     c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
                     c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
-                    c->d_flush};
+                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb};
     for (void *p : ptrs) cudaFree(p);
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_i32) cudaFreeHost(c->h_i32);
@@ -730,11 +739,9 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
         }
         CU(c, cudaMemcpyAsync(c->d_view_pick, c->h_i32 + 2 * R, sizeof(int32_t) * n_picks, cudaMemcpyHostToDevice, c->stream));
     }
-    if (!indices_yx || !view_index) {
-        Scope s(c, "pick");
-        launch_pick(c->d_pix, c->d_view_pick, R, n_picks, n_views, c->cfg.image_w, c->cfg.image_h, seed, indices_yx ? 0 : 1,
-                    view_index ? 0 : 1, c->stream);
-    }
+    c->gen_pix = indices_yx ? 0 : 1;       // missing picks are drawn inside the sampler (Philox)
+    c->gen_view = view_index ? 0 : 1;
+    c->pick_views = n_views;
     const float *dj = nullptr;
     if (jitter && randomize) {
         CU(c, cudaMemcpyAsync(c->d_jitter, jitter, sizeof(float) * (size_t)R * S, cudaMemcpyHostToDevice, c->stream));
@@ -828,7 +835,7 @@ int nerf_train_iter(nerf_ctx *c, uint64_t seed) {
     while (n_picks > 1 && c->R % n_picks != 0) --n_picks;   // largest pick count that splits R evenly
     int rc = nerf_get_batch(c, nullptr, nullptr, n_picks, nullptr, 1, seed, nullptr, nullptr, nullptr, nullptr, nullptr);
     if (rc) return rc;
-    rc = do_predict(c, 1, nullptr, nullptr);
+    rc = do_predict(c, 1, nullptr, nullptr, /*skip_composite=*/true);
     if (rc) return rc;
     return do_step(c, nullptr, 0, nullptr);
 }
@@ -849,19 +856,18 @@ int nerf_sync(nerf_ctx *c) {
     return check_launch(c, "sync");
 }
 
-int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed, float *out_rgba,
-                uint32_t *out_0rgb) {
-    if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+// Rows [y0, y1) of a frame at (yaw, pitch) into the context's device frame buffers (row y at offset y*W).
+static int render_rows_device(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed, bool pack) {
     const int W = c->cfg.image_w, H = c->cfg.image_h;
-    if (y0 < 0 || y1 > H || y0 >= y1) return fail(c, NERF_ERR_INVALID_ARG, "render: bad row range");
+    if (!c->d_frame_rgba) {
+        CU(c, cudaMalloc(&c->d_frame_rgba, sizeof(float) * 4 * (size_t)W * H));
+        CU(c, cudaMalloc(&c->d_frame_0rgb, sizeof(uint32_t) * (size_t)W * H));
+    }
     ViewPose vp;
     make_pose(yaw, pitch, vp);
     CU(c, cudaMemcpyAsync(c->d_render_pose, &vp, sizeof(vp), cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));  // vp is a stack temporary
     const int64_t total = (int64_t)(y1 - y0) * W;
-    uint32_t *d_packed = nullptr;
-    if (out_0rgb) CU(c, cudaMalloc(&d_packed, sizeof(uint32_t) * (size_t)c->R));
     c->batch_valid = false;
     c->predicted = false;
     c->acts_valid = false;
@@ -869,46 +875,67 @@ int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int
     int rc = NERF_OK;
     for (int64_t p0 = 0; p0 < total && rc == NERF_OK; p0 += saveR) {
         const int nr = (int)((total - p0 < saveR) ? total - p0 : saveR);
-        // pixel (y,x) list of this chunk, row-major (display.rs:58-62)
-        {
+        {   // pixel (y,x) list of this chunk, row-major (display.rs:58-62)
             Scope s(c, "frame_indices");
-            // indices for flat pixel range [p0, p0+nr): reuse the full-frame kernel on whole rows when aligned
-            const int ya = y0 + (int)(p0 / W), yb = y0 + (int)((p0 + nr + W - 1) / W);
-            if (p0 % W == 0 && (int64_t)(yb - ya) * W <= saveR) {
-                launch_full_frame_indices(c->d_pix, ya, yb, W, c->stream);
-            } else {
-                rc = ensure_i32(c, (size_t)2 * saveR + 1);
-                if (rc) break;
-                for (int i = 0; i < nr; ++i) {
-                    c->h_i32[2 * i] = y0 + (int)((p0 + i) / W);
-                    c->h_i32[2 * i + 1] = (int)((p0 + i) % W);
-                }
-                cudaMemcpyAsync(c->d_pix, c->h_i32, sizeof(int32_t) * 2 * nr, cudaMemcpyHostToDevice, c->stream);
-                cudaStreamSynchronize(c->stream);
-            }
+            launch_flat_pixel_indices(c->d_pix, (int64_t)y0 * W + p0, nr, W, c->stream);
         }
-        rc = run_sampler(c, nr, nullptr, 1, c->d_render_pose, 0, nullptr, randomize, seed, p0, false, false);
+        rc = run_sampler(c, nr, nullptr, 1, c->d_render_pose, 0, nullptr, randomize, seed, (int64_t)y0 * W + p0, false, false);
         if (rc) break;
         c->R = nr;  // temporarily narrow the batch view for the engines
         for (int r0 = 0; r0 < nr && rc == NERF_OK; r0 += c->chunk) {
             const int n2 = (nr - r0 < c->chunk) ? nr - r0 : c->chunk;
             rc = mlp_forward(c, r0, n2, 0);
         }
-        if (rc == NERF_OK) rc = composite_forward(c, nr, c->d_out);
+        float *dst = c->d_frame_rgba + 4 * ((size_t)y0 * W + p0);
+        if (rc == NERF_OK) rc = composite_forward(c, nr, dst);
         c->R = saveR;
         if (rc) break;
-        if (out_rgba) cudaMemcpyAsync(out_rgba + 4 * p0, c->d_out, sizeof(float) * 4 * nr, cudaMemcpyDeviceToHost, c->stream);
-        if (out_0rgb) {
+        if (pack) {
             Scope s(c, "pack_0rgb");
-            launch_pack_0rgb(c->d_out, d_packed, nr, c->stream);
-            cudaMemcpyAsync(out_0rgb + p0, d_packed, sizeof(uint32_t) * nr, cudaMemcpyDeviceToHost, c->stream);
+            launch_pack_0rgb(dst, c->d_frame_0rgb + (size_t)y0 * W + p0, nr, c->stream);
         }
     }
-    cudaError_t e = cudaStreamSynchronize(c->stream);
-    if (d_packed) cudaFree(d_packed);
     if (rc) return rc;
-    if (e != cudaSuccess) return fail(c, NERF_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
     return check_launch(c, "render");
+}
+
+int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed, float *out_rgba,
+                uint32_t *out_0rgb) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int W = c->cfg.image_w, H = c->cfg.image_h;
+    if (y0 < 0 || y1 > H || y0 >= y1) return fail(c, NERF_ERR_INVALID_ARG, "render: bad row range");
+    int rc = render_rows_device(c, yaw, pitch, y0, y1, randomize, seed, out_0rgb != nullptr);
+    if (rc) return rc;
+    const size_t n = (size_t)(y1 - y0) * W, off = (size_t)y0 * W;
+    if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_frame_rgba + 4 * off, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (out_0rgb) CU(c, cudaMemcpyAsync(out_0rgb, c->d_frame_0rgb + off, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "render");
+}
+
+int nerf_render_sharded(nerf_ctx *c, float yaw, float pitch, int32_t randomize, uint64_t seed, float *out_rgba, uint32_t *out_0rgb) {
+    if (!c) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int W = c->cfg.image_w, H = c->cfg.image_h, N = c->comm.nranks, r = c->comm.rank;
+    if (H % N != 0) return fail(c, NERF_ERR_INVALID_ARG, "render_sharded: image height must divide evenly among the ranks");
+    const int rows = H / N;
+    int rc = render_rows_device(c, yaw, pitch, r * rows, (r + 1) * rows, randomize, seed, out_0rgb != nullptr);
+    if (rc) return rc;
+    if (N > 1) {   // the one collective of the render path: gather the row bands (in place: band r already sits at its offset)
+        char eb[256] = {0};
+        Scope s(c, "render_allgather");
+        if (out_rgba && comm_allgather_bytes(c->comm, c->d_frame_rgba + 4 * (size_t)r * rows * W, c->d_frame_rgba, sizeof(float) * 4 * (size_t)rows * W,
+                                             c->stream, eb, sizeof(eb)))
+            return fail(c, NERF_ERR_COMM, eb);
+        if (out_0rgb && comm_allgather_bytes(c->comm, c->d_frame_0rgb + (size_t)r * rows * W, c->d_frame_0rgb, sizeof(uint32_t) * (size_t)rows * W,
+                                             c->stream, eb, sizeof(eb)))
+            return fail(c, NERF_ERR_COMM, eb);
+    }
+    if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_frame_rgba, sizeof(float) * 4 * (size_t)W * H, cudaMemcpyDeviceToHost, c->stream));
+    if (out_0rgb) CU(c, cudaMemcpyAsync(out_0rgb, c->d_frame_0rgb, sizeof(uint32_t) * (size_t)W * H, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return check_launch(c, "render_sharded");
 }
 
 int nerf_comm_unique_id(void *id128) {

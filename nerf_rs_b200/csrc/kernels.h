@@ -7,6 +7,8 @@ struct SampleArgs {
     const int32_t *pix_yx;     // [R][2] (y, x)
     const int32_t *view_pick;  // [n_picks] view ids, ray r uses view_pick[r / rays_per_pick]; NULL -> fixed_view
     int32_t rays_per_pick, fixed_view;
+    int32_t gen_pix, gen_view, n_views;   // != 0: draw the pixel / view picks here (Philox) and record them
+    int32_t *pix_out, *view_out;
     const ViewPose *poses;
     const float *jitter;       // [R][S] or NULL -> Philox
     const float *images;       // [V][H*W][4] or NULL
@@ -27,6 +29,7 @@ void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st);
 void launch_encode(const float *x, float *out, int64_t n, int freqs, int repeat, cudaStream_t st);
 void launch_pack_0rgb(const float *rgba, uint32_t *out, int64_t n, cudaStream_t st);
 void launch_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w, cudaStream_t st);
+void launch_flat_pixel_indices(int32_t *pix_yx, int64_t first, int n, int img_w, cudaStream_t st);
 
 // ---------------------------------------------------------------- composite.cu
 struct CompositeArgs {
@@ -44,6 +47,9 @@ struct CompositeArgs {
     float *ray_loss;           // [R] per-ray sum of squared errors
     float *d_sigma;            // [R][S]
     float *d_colors;           // [R][S][4]
+    float *loss_out;           // fused mean loss (last block reduces ray_loss in a fixed order), or NULL
+    float loss_scale;          // 1 / (4 R)
+    unsigned int *done_counter;  // zero-initialised, reset by the kernel
 };
 void launch_composite_fwd(const CompositeArgs &a, int num_sms, cudaStream_t st);
 void launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st);

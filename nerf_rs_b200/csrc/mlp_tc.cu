@@ -629,6 +629,38 @@ __global__ void k_pack_chunks(const PackChunk *chunks, const float *__restrict__
     }
 }
 
+// one launch for everything that follows an Adam step: forward chunk stream, backward (transposed) chunk stream, padded biases
+__global__ void k_pack_all(const PackChunk *fwd_chunks, int n_fwd, uint8_t *__restrict__ fwd_dst, const PackChunk *bwd_chunks, int n_bwd,
+                           uint8_t *__restrict__ bwd_dst, const PackBias *pb, int n_bias, const float *__restrict__ params,
+                           float *__restrict__ bias_dst) {
+    const int b = blockIdx.x;
+    if (b >= n_fwd + n_bwd) {
+        const PackBias e = pb[b - n_fwd - n_bwd];
+        for (int i = threadIdx.x; i < e.padded; i += blockDim.x) bias_dst[e.dst_off + i] = i < e.count ? params[e.src_base + i] : 0.f;
+        return;
+    }
+    const PackChunk pc = b < n_fwd ? fwd_chunks[b] : bwd_chunks[b - n_fwd];
+    uint8_t *dst = b < n_fwd ? fwd_dst : bwd_dst;
+    for (int i = threadIdx.x; i < pc.n_rows * 8; i += blockDim.x) {
+        const int r = i >> 3, c8 = i & 7;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c = c8 * 8 + 2 * e + h;
+                v[h] = (r < pc.valid_rows && c < pc.valid_cols)
+                           ? params[pc.src_base + (int64_t)r * pc.row_stride + (int64_t)c * pc.col_stride]
+                           : 0.f;
+            }
+            w[e] = ptx::pack_bf16x2(v[0], v[1]);
+        }
+        *reinterpret_cast<uint4 *>(dst + pc.dst_off + (uint32_t)r * 128u + (uint32_t)(((c8 ^ r) & 7) << 4)) =
+            make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 __global__ void k_pack_bias(const PackBias *pb, int n, const float *__restrict__ params, float *__restrict__ dst) {
     for (int b = blockIdx.x; b < n; b += gridDim.x) {
         const PackBias e = pb[b];
@@ -766,9 +798,10 @@ size_t tc_bytes_per_tile(const TcState *s) {
 const char *tc_last_error(const TcState *s) { return s->err.c_str(); }
 
 void tc_pack_weights(TcState *s, const float *params, cudaStream_t st) {
-    k_pack_chunks<<<s->fwd_train.n_chunks, 256, 0, st>>>(s->fwd_train.chunks, params, s->fwd_train.wpack);
-    k_pack_chunks<<<s->bwd.n_chunks, 256, 0, st>>>(s->bwd.chunks, params, s->bwd.wpack);
-    k_pack_bias<<<(int)s->plan.biases.size(), 128, 0, st>>>(s->d_pbias, (int)s->plan.biases.size(), params, s->d_bias);
+    const int nb = (int)s->plan.biases.size();
+    k_pack_all<<<s->fwd_train.n_chunks + s->bwd.n_chunks + nb, 256, 0, st>>>(s->fwd_train.chunks, s->fwd_train.n_chunks, s->fwd_train.wpack,
+                                                                              s->bwd.chunks, s->bwd.n_chunks, s->bwd.wpack, s->d_pbias, nb,
+                                                                              params, s->d_bias);
     ++s->bias_version;
 }
 

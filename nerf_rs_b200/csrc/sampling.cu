@@ -60,8 +60,24 @@ k_sample(SampleArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = a.num_samples;
     for (int r = blockIdx.x * kWarpsPerBlock + warp; r < a.num_rays; r += gridDim.x * kWarpsPerBlock) {
-        const int y = a.pix_yx[2 * r], x = a.pix_yx[2 * r + 1];
-        const int view = a.view_pick ? a.view_pick[r / a.rays_per_pick] : a.fixed_view;
+        // pixel / view picks: caller-supplied, or Philox in place (replaces Tensor::randint, dataset.rs:12,19,88)
+        int y, x;
+        if (a.gen_pix) {
+            y = min((int)(philox_uniform(a.seed, NERF_STREAM_PIX_Y, (uint64_t)r) * (float)a.img_h), a.img_h - 1);
+            x = min((int)(philox_uniform(a.seed, NERF_STREAM_PIX_X, (uint64_t)r) * (float)a.img_w), a.img_w - 1);
+            if (lane == 0) { a.pix_out[2 * r] = y; a.pix_out[2 * r + 1] = x; }
+        } else {
+            y = a.pix_yx[2 * r];
+            x = a.pix_yx[2 * r + 1];
+        }
+        int view = a.fixed_view;
+        if (a.gen_view) {
+            const int pick = r / a.rays_per_pick;
+            view = min((int)(philox_uniform(a.seed, NERF_STREAM_VIEW, (uint64_t)pick) * (float)a.n_views), a.n_views - 1);
+            if (lane == 0 && r % a.rays_per_pick == 0) a.view_out[pick] = view;
+        } else if (a.view_pick) {
+            view = a.view_pick[r / a.rays_per_pick];
+        }
         const ViewPose vp = a.poses[view];
         float to[3];
         screen_to_world((float)x, (float)y, (float)a.img_w, (float)a.img_h, a.off, to);
@@ -172,6 +188,15 @@ __global__ void k_pack_0rgb(const float *__restrict__ rgba, uint32_t *__restrict
     out[i] = (c[0] << 16) | (c[1] << 8) | c[2];
 }
 
+// pixel (y, x) of the flat row-major pixel range [first, first + n)
+__global__ void k_flat_pixel_indices(int32_t *pix_yx, int64_t first, int n, int img_w) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t p = first + i;
+    pix_yx[2 * i] = (int)(p / img_w);
+    pix_yx[2 * i + 1] = (int)(p % img_w);
+}
+
 __global__ void k_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t n = (int64_t)(y1 - y0) * img_w;
@@ -205,6 +230,11 @@ void launch_encode(const float *x, float *out, int64_t n, int freqs, int repeat,
 void launch_pack_0rgb(const float *rgba, uint32_t *out, int64_t n, cudaStream_t st) {
     if (n <= 0) return;
     k_pack_0rgb<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rgba, out, n);
+}
+
+void launch_flat_pixel_indices(int32_t *pix_yx, int64_t first, int n, int img_w, cudaStream_t st) {
+    if (n <= 0) return;
+    k_flat_pixel_indices<<<(n + 255) / 256, 256, 0, st>>>(pix_yx, first, n, img_w);
 }
 
 void launch_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w, cudaStream_t st) {

@@ -123,3 +123,14 @@ def test_fused_sampling_in_the_mlp_prologue_is_bit_identical(s):
     assert np.array_equal(sig_a, sig_b) and np.array_equal(out_a, out_b)
     out_c, sig_c = m.predict(b["points"].reshape(-1), b["t"].reshape(-1), b["dirs"].reshape(-1), train=False)   # literal signature
     assert np.array_equal(sig_a, sig_c) and np.array_equal(out_a, out_c)
+
+
+def test_render_sharded_single_rank_equals_render():
+    """Without a communicator the sharded render is one band: identical to nerf_render of the whole frame."""
+    cfg = nb.default_config(image_w=48, image_h=40, num_rays=512, num_samples=24, hidden=64)
+    m = nb.NeRF(cfg)
+    full, pk = m.render(0.4, 0.3, packed=True)
+    sh, pks = m.render_sharded(0.4, 0.3, packed=True)
+    assert np.array_equal(full, sh) and np.array_equal(pk, pks)
+    part = m.render(0.4, 0.3, 7, 19)                 # an unaligned row band equals the same rows of the full frame
+    assert np.array_equal(part, full[7:19])
