@@ -6,6 +6,8 @@
 //   denom = sqrt(v)/sqrt(1-b2^t) + eps;  p -= (lr/(1-b1^t)) * m/denom.
 // HBM-bound: p,m,v read+write, g read (+ zeroed for the next step) = 28(+4) B/param.
 // grad_scale folds the 1/nranks of the data-parallel all-reduce.
+#include <cstdio>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -48,6 +50,88 @@ __global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
     }
 }
 
+// ---- fused all-reduce + Adam over peer memory ------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float *p) {   // peer memory: do not keep in L1
+    float4 v;
+    asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_adam_p2p(const __grid_constant__ AdamP2PArgs a) {
+    // 1. publish "my gradient for `step` is complete" (the weight-gradient kernel precedes this one in the stream) in
+    //    every rank's flag array, slot = my rank
+    if (blockIdx.x == 0 && (int)threadIdx.x < a.nranks) {
+        __threadfence_system();
+        st_release_sys(a.peer_flags[threadIdx.x] + a.rank, a.step);
+    }
+    // 2. wait until every rank has published this step (local polls; a dead peer becomes a trap, not a hang)
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < a.nranks; ++r) {
+            unsigned int spins = 0;
+            while ((int)(ld_acquire_sys(a.my_flags + r) - a.step) < 0) {
+                if (++spins > (1u << 27)) {
+                    printf("nerf_b200: peer gradient flag timeout (rank %d waiting for rank %d, step %u)\n", a.rank, r, a.step);
+                    __trap();
+                }
+                __nanosleep(64);
+            }
+        }
+    }
+    __syncthreads();
+    // 3. sum the peers' gradients in rank order and apply Adam to my replica
+    const AdamArgs &ad = a.adam;
+    const int64_t n4 = ad.n >> 2;
+    const float omb1 = 1.f - ad.beta1, omb2 = 1.f - ad.beta2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        // all peer loads in flight together (NVLink round trips overlap), then a fixed rank-order sum
+        float4 t[NERF_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < NERF_MAX_RANKS; ++r)
+            t[r] = r < a.nranks ? ld_peer_f4(a.peer_grads[r] + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = t[0];
+#pragma unroll
+        for (int r = 1; r < NERF_MAX_RANKS; ++r) { g.x += t[r].x; g.y += t[r].y; g.z += t[r].z; g.w += t[r].w; }
+        float4 p = reinterpret_cast<float4 *>(ad.p)[i];
+        float4 m = reinterpret_cast<float4 *>(ad.m)[i];
+        float4 v = reinterpret_cast<float4 *>(ad.v)[i];
+        float *pp = &p.x, *mm = &m.x, *vv = &v.x, *gg = &g.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gg[k] * ad.grad_scale;
+            mm[k] = mm[k] * ad.beta1 + gr * omb1;
+            vv[k] = vv[k] * ad.beta2 + omb2 * gr * gr;
+            const float denom = sqrtf(vv[k]) * ad.inv_sqrt_bc2 + ad.eps;
+            pp[k] = pp[k] - ad.lr_over_bc1 * (mm[k] / denom);
+        }
+        reinterpret_cast<float4 *>(ad.p)[i] = p;
+        reinterpret_cast<float4 *>(ad.m)[i] = m;
+        reinterpret_cast<float4 *>(ad.v)[i] = v;
+        reinterpret_cast<float4 *>(ad.g)[i] = g;      // the summed gradient, like ncclAllReduce leaves it
+    }
+    if (blockIdx.x == 0) {   // tail (n % 4)
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < ad.n; i += blockDim.x) {
+            float g = 0.f;
+            for (int r = 0; r < a.nranks; ++r) g += *reinterpret_cast<const volatile float *>(a.peer_grads[r] + i);
+            const float gr = g * ad.grad_scale;
+            const float m = ad.m[i] * ad.beta1 + gr * omb1;
+            const float v = ad.v[i] * ad.beta2 + omb2 * gr * gr;
+            const float denom = sqrtf(v) * ad.inv_sqrt_bc2 + ad.eps;
+            ad.p[i] = ad.p[i] - ad.lr_over_bc1 * (m / denom);
+            ad.m[i] = m;
+            ad.v[i] = v;
+            ad.g[i] = g;
+        }
+    }
+}
+
 // U(-1/sqrt(in), 1/sqrt(in)) for weights and biases -- the bound nn.Linear / tch nn::linear
 // defaults use (kaiming_uniform(a=sqrt(5)) reduces to it). Exact values are irrelevant once
 // set_weights injects a blob; this only makes a fresh context trainable.
@@ -71,6 +155,14 @@ void launch_adam(const AdamArgs &a, int num_sms, cudaStream_t st) {
     if (blocks > num_sms * 8) blocks = num_sms * 8;
     if (blocks < 1) blocks = 1;
     k_adam<<<blocks, 256, 0, st>>>(a);
+}
+
+void launch_adam_p2p(const AdamP2PArgs &a, int num_sms, cudaStream_t st) {
+    int64_t n4 = a.adam.n >> 2;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks > num_sms * 4) blocks = num_sms * 4;
+    if (blocks < 1) blocks = 1;
+    k_adam_p2p<<<blocks, 256, 0, st>>>(a);
 }
 
 void launch_init_uniform(float *p, const NetGeom &g, uint64_t seed, cudaStream_t st) {

@@ -92,6 +92,7 @@ struct nerf_ctx {
 
     // parameters
     float *d_params = nullptr, *d_grads = nullptr, *d_m = nullptr, *d_v = nullptr;
+    float *d_gacc[2] = {nullptr, nullptr};   // peer-memory data parallelism: local gradient accumulation buffers, alternating per step
     int64_t step = 0;
     bool weights_dirty = true;
 
@@ -288,16 +289,16 @@ int mlp_forward(nerf_ctx *c, int r0, int nr, int train) {
     return check_launch(c, "mlp_forward");
 }
 
-int mlp_backward(nerf_ctx *c, int r0, int nr) {
+int mlp_backward(nerf_ctx *c, int r0, int nr, float *grads) {
     const int64_t n = (int64_t)nr * c->S;
     const int64_t s0 = (int64_t)r0 * c->S;
     if (is_tc(c->cfg.mlp_impl)) {
-        if (tc_backward(c->tc, c->d_rgba + 4 * s0, c->d_dsigma + s0, c->d_drgba + 4 * s0, n, c->d_grads, c->stream,
+        if (tc_backward(c->tc, c->d_rgba + 4 * s0, c->d_dsigma + s0, c->d_drgba + 4 * s0, n, grads, c->stream,
                         prof_between, c))
             return fail(c, NERF_ERR_INVALID_ARG, tc_last_error(c->tc));
     } else {
         Scope s(c, "mlp_bwd_simt", 30);
-        simt_mlp_backward(c->g, c->d_params, c->d_grads, nr, c->S, c->cfg.mlp_impl == NERF_MLP_SIMT ? 1 : 0, c->simt,
+        simt_mlp_backward(c->g, c->d_params, grads, nr, c->S, c->cfg.mlp_impl == NERF_MLP_SIMT ? 1 : 0, c->simt,
                           c->d_rgba + 4 * s0, c->d_dsigma + s0, c->d_drgba + 4 * s0, c->stream);
     }
     return check_launch(c, "mlp_backward");
@@ -369,20 +370,24 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     }
     int rc = check_launch(c, "composite_bwd");
     if (rc) return rc;
-    // gradients accumulate (+=) over micro-batches and weight-gradient CTAs: start from zero
-    CU(c, cudaMemsetAsync(c->d_grads, 0, sizeof(float) * c->g.n_params, c->stream));
+    // gradients accumulate (+=) over micro-batches and weight-gradient CTAs: start from zero.
+    // With the peer-memory all-reduce the local gradient goes to one of two buffers the other ranks read directly; a
+    // buffer is reused two steps later, after every peer has passed the next step's hand-shake.
+    const bool p2p = nranks > 1 && c->comm.p2p;
+    float *gacc = p2p ? c->d_gacc[(c->comm.p2p_step + 1) & 1] : c->d_grads;
+    CU(c, cudaMemsetAsync(gacc, 0, sizeof(float) * c->g.n_params, c->stream));
     for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
         const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
         if (!c->acts_valid) {
             rc = mlp_forward(c, r0, nr, 1);  // recompute this micro-batch's activations
             if (rc) return rc;
         }
-        rc = mlp_backward(c, r0, nr);
+        rc = mlp_backward(c, r0, nr, gacc);
         if (rc) return rc;
     }
     c->acts_valid = false;
     c->predicted = false;
-    if (nranks > 1) {
+    if (nranks > 1 && !p2p) {
         Scope s(c, "grad_allreduce");
         char eb[256] = {0};
         if (comm_allreduce_sum_f32(c->comm, c->d_grads, c->g.n_params, c->stream, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
@@ -399,8 +404,26 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         a.beta1 = c->cfg.beta1; a.beta2 = c->cfg.beta2; a.eps = c->cfg.eps;
         a.grad_scale = 1.f / (float)nranks;
         a.zero_grad = 0;
-        Scope s(c, "adam");
-        launch_adam(a, c->num_sms, c->stream);
+        if (p2p) {
+            // ONE kernel: cross-GPU hand-shake, sum of all ranks' gradients over NVLink peer loads (rank order), Adam
+            AdamP2PArgs pa;
+            memset(&pa, 0, sizeof(pa));
+            pa.adam = a;
+            const unsigned int pstep = ++c->comm.p2p_step;
+            for (int r = 0; r < nranks; ++r) {
+                pa.peer_grads[r] = c->comm.peer_grads[pstep & 1][r];
+                pa.peer_flags[r] = c->comm.peer_flags[r];
+            }
+            pa.my_flags = c->comm.my_flags;
+            pa.rank = c->comm.rank;
+            pa.nranks = nranks;
+            pa.step = pstep;
+            Scope s(c, "adam_allreduce_p2p");
+            launch_adam_p2p(pa, c->num_sms, c->stream);
+        } else {
+            Scope s(c, "adam");
+            launch_adam(a, c->num_sms, c->stream);
+        }
     }
     c->weights_dirty = true;
     rc = ensure_packed(c);
@@ -510,7 +533,7 @@ int nerf_destroy(nerf_ctx *c) {
     void *ptrs[] = {c->d_params, c->d_grads, c->d_m, c->d_v, c->d_images, c->d_poses, c->d_render_pose, c->d_pix, c->d_view_pick,
                     c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
                     c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
-                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb};
+                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1]};
     for (void *p : ptrs) cudaFree(p);
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_i32) cudaFreeHost(c->h_i32);
@@ -953,6 +976,17 @@ int nerf_comm_init_rank(nerf_ctx *c, const void *id128, int32_t rank, int32_t nr
     CU(c, cudaSetDevice(c->device));
     char eb[256] = {0};
     if (comm_init_rank(c->comm, id128, rank, nranks, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
+    // peer-memory gradient exchange (fused all-reduce + Adam); NERF_B200_P2P=0 keeps the plain NCCL all-reduce
+    const char *env = getenv("NERF_B200_P2P");
+    if (nranks > 1 && nranks <= NERF_MAX_RANKS && !(env && env[0] == '0')) {
+        const size_t bytes = sizeof(float) * ((c->g.n_params + 3) / 4 * 4);
+        for (int b = 0; b < 2; ++b) {
+            if (!c->d_gacc[b]) CU(c, cudaMalloc(&c->d_gacc[b], bytes));
+            CU(c, cudaMemsetAsync(c->d_gacc[b], 0, bytes, c->stream));
+        }
+        if (comm_p2p_setup(c->comm, c->d_gacc[0], c->d_gacc[1], c->stream, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
+        if (!c->comm.p2p && eb[0]) c->err = eb;   // informational: fell back to NCCL
+    }
     return NERF_OK;
 }
 

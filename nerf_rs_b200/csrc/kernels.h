@@ -63,6 +63,22 @@ struct AdamArgs {
     int32_t zero_grad;
 };
 void launch_adam(const AdamArgs &a, int num_sms, cudaStream_t st);
+
+// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel training, one process per GPU).
+// Every rank reads all ranks' local gradient buffers directly (peer pointers opened with CUDA IPC), sums them in
+// rank order -- so every replica applies bit-identical updates -- and runs Adam on its own copy of the parameters.
+// Cross-GPU hand-shake: monotonic step counters in each rank's flag array (flags[r] = last step for which rank r's
+// gradient is complete), written remotely with system-scope release stores and polled locally.
+#define NERF_MAX_RANKS 8
+struct AdamP2PArgs {
+    AdamArgs adam;                        // adam.g = where the summed gradient is written back (nerf_get_grads)
+    const float *peer_grads[NERF_MAX_RANKS];   // rank r's local gradient buffer for this step (index == rank)
+    unsigned int *peer_flags[NERF_MAX_RANKS];  // rank r's flag array [NERF_MAX_RANKS]
+    unsigned int *my_flags;
+    int32_t rank, nranks;
+    uint32_t step;                        // > 0, monotonic
+};
+void launch_adam_p2p(const AdamP2PArgs &a, int num_sms, cudaStream_t st);
 void launch_init_uniform(float *p, const NetGeom &g, uint64_t seed, cudaStream_t st);
 
 // ---------------------------------------------------------------- mlp_simt.cu
