@@ -557,7 +557,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NERF_ERR_NO_DEVICE;
     if (prop.major != 10) return NERF_ERR_NO_DEVICE;  // kernels are built for sm_100a only
-    if (cfg->num_rays < 1 || cfg->num_samples < 1 || cfg->num_samples > 256 || cfg->hidden < 2 || cfg->hidden > 256 ||
+    if (cfg->num_rays < 1 || cfg->num_samples < 1 || cfg->num_samples > 256 || cfg->hidden < 2 || cfg->hidden > 512 ||
         cfg->xyz_freqs < 0 || cfg->xyz_freqs > 10 || cfg->dir_freqs > 4 || cfg->image_w < 1 || cfg->image_h < 1 ||
         cfg->mlp_impl < 0 || cfg->mlp_impl > 3 || cfg->depth_mode < 0 || cfg->depth_mode > 1)
         return NERF_ERR_UNSUPPORTED;

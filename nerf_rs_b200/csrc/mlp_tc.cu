@@ -727,7 +727,9 @@ TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version
     s->max_tiles = max_tiles;
     s->version = version;
     if (!tc_build_plan(g, s->plan, err)) { delete s; return nullptr; }
+    if (s->plan.np > 4 && version != 2) { err = "hidden > 256 needs the CTA-pair kernel (NERF_MLP_TCGEN05)"; delete s; return nullptr; }
     for (const TcProgram *p : {&s->plan.fwd_train, &s->plan.fwd_infer, &s->plan.bwd}) {
+        if (version != 1) break;
         const size_t need = ((s->plan.bias_floats * 4 + 15) & ~15u) + ((p->ops.size() * sizeof(MmaOp) + 15) & ~15u) + p->jobs.size() * sizeof(EpiJob);
         if (need > kTableBytes) { err = "tc_create: program tables exceed the shared-memory table area"; delete s; return nullptr; }
     }
@@ -742,7 +744,7 @@ TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version
     if (max_tiles > 0) {
         ok = ok && cudaMalloc(&s->d_act, (size_t)max_tiles * s->plan.act_slots * kSlotBytes) == cudaSuccess;
         ok = ok && cudaMalloc(&s->d_grad, (size_t)max_tiles * s->plan.grad_slots * kSlotBytes) == cudaSuccess;
-        ok = ok && cudaMalloc(&s->d_mask, (size_t)max_tiles * s->plan.mask_slots * NERF_TILE_M * 8 * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && cudaMalloc(&s->d_mask, (size_t)max_tiles * s->plan.mask_slots * NERF_TILE_M * s->plan.mask_words * sizeof(uint32_t)) == cudaSuccess;
     }
     ok = ok && cudaFuncSetAttribute(k_chain<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_chain<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmem) == cudaSuccess;
@@ -792,7 +794,7 @@ void tc_destroy(TcState *s) {
 }
 
 size_t tc_bytes_per_tile(const TcState *s) {
-    return (size_t)(s->plan.act_slots + s->plan.grad_slots) * kSlotBytes + (size_t)s->plan.mask_slots * NERF_TILE_M * 32;
+    return (size_t)(s->plan.act_slots + s->plan.grad_slots) * kSlotBytes + (size_t)s->plan.mask_slots * NERF_TILE_M * 4 * s->plan.mask_words;
 }
 
 const char *tc_last_error(const TcState *s) { return s->err.c_str(); }
@@ -828,6 +830,7 @@ int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, in
         }
         l.save_base = train ? s->d_act : nullptr; l.save_slots = s->plan.act_slots;
         l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
+        l.wide = s->plan.np > 4; l.e_slot = s->plan.e_slot; l.mask_words = s->plan.mask_words;
         tc2_launch(train ? s->fwd_train2 : s->fwd_infer2, l, st);
         return 0;
     }
@@ -921,6 +924,7 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
         l.rgba = const_cast<float *>(rgba); l.d_sigma = d_sigma; l.d_rgba = d_rgba;
         l.save_base = s->d_grad; l.save_slots = s->plan.grad_slots;
         l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
+        l.wide = s->plan.np > 4; l.e_slot = s->plan.e_slot; l.mask_words = s->plan.mask_words;
         tc2_launch(s->bwd2, l, st);
     } else
         k_chain<true, true><<<grid, kChainThreads, kChainSmem, st>>>(a);
@@ -942,8 +946,8 @@ int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaS
     if (area == 0 && slot < s->plan.act_slots) src = s->d_act + ((size_t)tile * s->plan.act_slots + slot) * kSlotBytes;
     else if (area == 1 && slot < s->plan.grad_slots) src = s->d_grad + ((size_t)tile * s->plan.grad_slots + slot) * kSlotBytes;
     else if (area == 2 && slot < s->plan.mask_slots) {
-        src = s->d_mask + ((size_t)tile * s->plan.mask_slots + slot) * NERF_TILE_M * 8;
-        bytes = NERF_TILE_M * 8 * sizeof(uint32_t);
+        src = s->d_mask + ((size_t)tile * s->plan.mask_slots + slot) * NERF_TILE_M * s->plan.mask_words;
+        bytes = NERF_TILE_M * s->plan.mask_words * sizeof(uint32_t);
     }
     if (!src) return -1;
     if (cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
@@ -973,6 +977,7 @@ int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n
         l.save_base = program == 0 ? s->d_act : (program == 2 ? s->d_grad : nullptr);
         l.save_slots = program == 2 ? s->plan.grad_slots : s->plan.act_slots;
         l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;
+        l.wide = s->plan.np > 4; l.e_slot = s->plan.e_slot; l.mask_words = s->plan.mask_words;
         l.trace = d_trace;
         tc2_launch(program == 0 ? s->fwd_train2 : (program == 1 ? s->fwd_infer2 : s->bwd2), l, st);
         cudaMemcpyAsync(host_out, d_trace, bytes, cudaMemcpyDeviceToHost, st);

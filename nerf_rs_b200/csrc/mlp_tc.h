@@ -15,6 +15,7 @@
 
 // smem A-operand slots (16 KB panels): hidden panels 0..3 (rewritten in place), E = encoded inputs
 #define TC_SLOT_E 4
+#define TC_SLOT_E_WIDE 8   // hidden 257..512 (pair kernel only): hidden panels 0..7, encoded inputs in slot 8
 #define TC_NUM_SLOTS 5
 #define TC_NUM_STAGES 4
 #define TC_STAGE_BYTES 32768   // one weight chunk [N <= 256][64 bf16]
@@ -31,6 +32,7 @@
 // MmaOp.flags
 #define TC_OP_FIRST 1u       // first K step of this accumulator block overwrites (accumulate = 0)
 #define TC_OP_COMMIT_ACC 2u  // commit to acc_full[acc] after this op
+#define TC_OP_GEMM_START 4u  // first op of a GEMM (a wide GEMM has a second TC_OP_FIRST op: its second 256-column half)
 
 struct MmaOp {
     uint32_t w_off;   // byte offset of the weight chunk in the packed stream
@@ -106,6 +108,7 @@ struct PackBias {
 };
 
 struct TcProgram {
+    bool wide = false;        // hidden 257..512 (see TC_SLOT_E_WIDE)
     std::vector<MmaOp> ops;
     std::vector<EpiJob> jobs;
     std::vector<PackChunk> chunks;
@@ -119,15 +122,19 @@ struct TcPlan {
     std::vector<WgradUnit> units;
     int act_slots = 0, grad_slots = 0, mask_slots = 0;
     int np = 0, np2 = 0;  // hidden panels, fc9-output panels
+    int e_slot = TC_SLOT_E, mask_words = 8;   // smem slot of the encoded inputs; 32-bit ReLU mask words per row and layer
 };
 
 // ---- v2 (mlp_tc2.cu): CTA-pair chain, two tiles ("lanes") in flight per CTA. The lane program is the v1
 // program regrouped per GEMM: one op list slice and ONE epilogue job per GEMM, plus the tile prologue (job 0).
+#define LANE_OP_KCOUNT 0x07u   // K16 steps (1, 2 or 4)
+#define LANE_OP_HALF1 0x40u    // accumulate into TMEM columns +256 (second half of a wide GEMM)
+#define LANE_OP_FIRST 0x80u    // first K step of its accumulator block: overwrite instead of accumulate
 struct LaneOp {
     uint32_t w_off;   // byte offset of the full chunk; CTA rank r of the pair loads rows [r n/2, (r+1) n/2)
     uint16_t n;       // MMA N (multiple of 16)
     uint8_t a_slot;   // lane-relative smem slot of the A operand
-    uint8_t kcount;   // K16 steps (1, 2 or 4)
+    uint8_t kflags;   // LANE_OP_*
 };
 struct LaneGemm {
     uint16_t op_begin, op_end;
@@ -166,6 +173,7 @@ struct Chain2Launch {
     int32_t save_slots;
     uint32_t *mask_base;
     int32_t mask_slots;
+    int32_t wide, e_slot, mask_words;
     unsigned long long *trace;   // debug: [3][2048][4] clock64 stamps of CTA 0, or NULL
 };
 void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st);

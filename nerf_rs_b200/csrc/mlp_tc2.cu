@@ -48,14 +48,15 @@ static_assert(kChain2Smem <= 232448, "exceeds the 227 KB per-CTA shared memory l
 constexpr int kEpiWarps = 16;                 // 4 lane quarters x kSplit column slices
 constexpr int kSplit = kEpiWarps / 4;
 constexpr int kThreads = 32 * (4 + kEpiWarps);
-constexpr int kMaxOps = 48, kMaxGemms = 16;
+constexpr int kMaxOps = 160, kMaxGemms = 16;
+constexpr int kMaxGroups = 16 / kSplit;       // 32-column groups per column slice of the widest (512-column) accumulator
 
 // Padded biases live in the constant bank: the epilogue adds them with warp-uniform constant loads, which -- unlike
 // ld.shared -- do not queue behind the tensor core's operand reads (tools/ubench_epi.cu: a 128x256 epilogue with
 // smem biases takes 1071 cycles on an idle SM but 2486 with MMAs in flight; without the bias loads 697 either way).
 // kBiasSlots contexts of one process can hold their biases side by side (tc2_bias_upload arbitrates).
-constexpr int kBiasSlots = 4;
-constexpr int kBiasSlotFloats = 2560;
+constexpr int kBiasSlots = 3;
+constexpr int kBiasSlotFloats = 4608;   // hidden 512: 7*512 + 16 + 512 + 256 + 16 = 4384 padded floats
 __constant__ float c_bias[kBiasSlots * kBiasSlotFloats];
 
 struct Chain2Args {
@@ -65,6 +66,8 @@ struct Chain2Args {
     LaneGemm gemms[kMaxGemms];
     LaneJob jobs[kMaxGemms + 1];   // job 0 = tile prologue
     int32_t n_ops, n_gemms;
+    int32_t wide;             // hidden 257..512: ONE lane per CTA (8 hidden panels + slot E = 8), 512-column accumulators
+    int32_t e_slot, mask_words;
     const uint8_t *wpack;
     const float *bias;
     int32_t bias_floats, bias_slot;
@@ -101,20 +104,21 @@ __device__ __forceinline__ void trace4(const Chain2Args &a, int role, int idx, u
 // (producer, relay, MMA issuer, epilogue) derives its order from this one deterministic schedule.
 struct LaneSched {
     int pair0, pair1;     // current pair-tile of lane 0 / lane 1 (lane l starts at cluster + l*C, stride 2C)
-    int pos, stride, n_pairs, n_pos;
-    __device__ LaneSched(int cluster, int n_clusters, int n_pairs_, int n_pos_)
-        : pair0(cluster), pair1(cluster + n_clusters), pos(0), stride(2 * n_clusters), n_pairs(n_pairs_), n_pos(n_pos_) {}
+    int pos, stride, n_pairs, n_pos, wide;   // wide: a single lane per CTA walks every pair tile of the cluster (stride C)
+    __device__ LaneSched(int cluster, int n_clusters, int n_pairs_, int n_pos_, int wide_)
+        : pair0(cluster), pair1(cluster + n_clusters), pos(0), stride(wide_ ? n_clusters : 2 * n_clusters), n_pairs(n_pairs_),
+          n_pos(n_pos_), wide(wide_) {}
     // next group: GEMM index g, number of live lanes (1 or 2: lane 1 never outlives lane 0), their pair tiles
     __device__ bool next(int &g, int &n_lanes, int &pr0, int &pr1) {
         if (pair0 >= n_pairs) return false;
         g = pos;
         pr0 = pair0;
         pr1 = pair1;
-        n_lanes = pair1 < n_pairs ? 2 : 1;
+        n_lanes = (!wide && pair1 < n_pairs) ? 2 : 1;
         if (++pos == n_pos) {
             pos = 0;
             pair0 += stride;
-            pair1 += stride;
+            if (!wide) pair1 += stride;
         }
         return true;
     }
@@ -218,10 +222,9 @@ __device__ __forceinline__ void store_group(uint32_t lane_base, uint32_t out_slo
 // (with four warps per scheduler the other warps cover the TMEM-load and store latencies).
 template <bool kSave, uint8_t kKind>
 __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uint32_t lane_base, int bias_base, uint32_t *mask_row,
-                                           uint32_t row, int G0, int G1, const uint32_t (&pm)[8 / kSplit]) {
-    static_assert(8 / kSplit == 2, "a column slice is at most two 32-column groups");
+                                           uint32_t row, int G0, int G1, const uint32_t (&pm)[kMaxGroups]) {
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {          // unrolled: G stays in the uniform datapath
+    for (int g = 0; g < kMaxGroups; ++g) {  // unrolled: G stays in the uniform datapath (2 groups per warp; 4 for a 512-column job)
         const int G = G0 + g;
         if (G < G1) {
             uint32_t r[32];
@@ -291,7 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         //       GEMM is shareable, once per lane otherwise
         // ===== warp 1 of the peer: relays "my half landed" to the leader's MMA thread, in the same order
         const bool producer = warp == 0;
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
         uint32_t stage = 0, phase = 0;
         int g, nl, pr0, pr1, ev = 0;
         while (sch.next(g, nl, pr0, pr1)) {
@@ -320,7 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         }
     } else if (warp == 1) {
         // ================= leader: MMA issuer for the pair =================
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
         uint32_t stage = 0, phase = 0;   // next stage to be consumed for the first time
         uint32_t done_phase = 0;         // bit l: parity to wait for on EPI_DONE[l]
         int mma_ev = 0;
@@ -348,15 +351,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     const uint32_t a_addr = sbase + (uint32_t)ln * kLaneBytes + (uint32_t)op.a_slot * kSlotBytes;
                     const uint32_t b_addr = sbase + kSmemSlots + stage * kStageBytes;
                     const uint32_t idesc = ptx::umma_idesc_bf16(256, op.n, 0, 0);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)ln * 256u;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)ln * 256u + ((op.kflags & LANE_OP_HALF1) ? 256u : 0u);
                     const uint64_t ad0 = ptx::umma_desc_sw128(a_addr, 16, 1024);
                     const uint64_t bd0 = ptx::umma_desc_sw128(b_addr, 16, 1024);
-                    const uint32_t acc0 = (i == gm.op_begin) ? 0u : 1u;
+                    const uint32_t acc0 = (op.kflags & LANE_OP_FIRST) ? 0u : 1u;
+                    const uint32_t kcount = op.kflags & LANE_OP_KCOUNT;
                     if (ptx::elect_one()) {
                         // +32 B per K16 step == +2 in the descriptor's address field
                         ptx::umma_ss2(d_tmem, ad0, bd0, idesc, acc0);
-                        if (op.kcount > 1) ptx::umma_ss2(d_tmem, ad0 + 2u, bd0 + 2u, idesc, 1u);
-                        if (op.kcount > 2) {
+                        if (kcount > 1) ptx::umma_ss2(d_tmem, ad0 + 2u, bd0 + 2u, idesc, 1u);
+                        if (kcount > 2) {
                             ptx::umma_ss2(d_tmem, ad0 + 4u, bd0 + 4u, idesc, 1u);
                             ptx::umma_ss2(d_tmem, ad0 + 6u, bd0 + 6u, idesc, 1u);
                         }
@@ -373,7 +377,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         // ================= store warp (training): bulk-stores every step's panels to the per-tile save area ==========
         // Steps arrive in the epilogue's order. A lane's panels may be rewritten once its stores have finished READING
         // shared memory (SAVE_FREE); the global writes themselves only have to land before the kernel ends.
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
         uint32_t rph = 0;   // bit l: parity to wait for on SAVE_READY[l]
         const LaneJob pj = s_jobs[0];
         int p, nl, pr0, pr1;
@@ -394,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                 const bool first_tile = pr < sch.stride;
                 const bool has_next = pr + sch.stride < a.n_pairs;
                 const uint32_t lane_base = sbase + (uint32_t)ln * kLaneBytes;
-                const uint32_t e_addr = lane_base + TC_SLOT_E * kSlotBytes;
+                const uint32_t e_addr = lane_base + (uint32_t)a.e_slot * kSlotBytes;
                 uint8_t *tile_base = a.save_base + (size_t)(2 * pr + (int)rank) * a.save_slots * kSlotBytes;
                 uint8_t *next_base = a.save_base + (size_t)(2 * (pr + sch.stride) + (int)rank) * a.save_slots * kSlotBytes;
                 if (p == 0 && first_tile)
@@ -404,9 +408,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                 const LaneJob j = s_jobs[p + 1];
                 store_step(ln, [&]() {
                     // consecutive panels are contiguous both in shared memory and in the save area: one copy
-                    if (j.save_slot >= 0)
-                        ptx::bulk_s2g(tile_base + (size_t)j.save_slot * kSlotBytes, lane_base + (uint32_t)j.out_slot * kSlotBytes,
-                                      (uint32_t)(j.ncols >> 6) * kSlotBytes);
+                    if (j.save_slot >= 0) {
+                        for (int p4 = 0; p4 < (j.ncols >> 6); p4 += 4) {   // <= 64 KB per copy
+                            const int np4 = (j.ncols >> 6) - p4 < 4 ? (j.ncols >> 6) - p4 : 4;
+                            ptx::bulk_s2g(tile_base + (size_t)(j.save_slot + p4) * kSlotBytes,
+                                          lane_base + (uint32_t)(j.out_slot + p4) * kSlotBytes, (uint32_t)np4 * kSlotBytes);
+                        }
+                    }
                     if (j.enc_save_slot >= 0) ptx::bulk_s2g(tile_base + (size_t)j.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
                     if (p == a.n_gemms - 1 && has_next && pj.enc_save_slot >= 0)
                         ptx::bulk_s2g(next_base + (size_t)pj.enc_save_slot * kSlotBytes, e_addr, kSlotBytes);
@@ -471,7 +479,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             if (a.trace) ts_b = clock64();
             if (lane_id == 0) ptx::mbar_arrive_cluster(done_bar0 + 8u * (uint32_t)ln);
         };
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
         int epi_ev = 0;
         int p, nl, pr0, pr1;
         while (sch.next(p, nl, pr0, pr1)) {
@@ -480,7 +488,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             const bool first_tile = pr < sch.stride;
             const bool has_next = pr + sch.stride < a.n_pairs;
             const uint32_t lane_base = sbase + (uint32_t)ln * kLaneBytes;
-            const uint32_t e_addr = lane_base + TC_SLOT_E * kSlotBytes;
+            const uint32_t e_addr = lane_base + (uint32_t)a.e_slot * kSlotBytes;
             const int tile = 2 * pr + (int)rank;
             const int64_t gs = (int64_t)tile * NERF_TILE_M + row;
             const bool valid = gs < a.n_samples;
@@ -510,12 +518,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             const int G0 = h * gpw < NG ? h * gpw : NG;
             const int G1 = G0 + gpw < NG ? G0 + gpw : NG;
             uint32_t *mask_row = nullptr;
-            uint32_t pm[8 / kSplit];
+            uint32_t pm[kMaxGroups];
             if (j.mask_slot >= 0 && j.kind != EK_SIGMA && j.kind != EK_RGBA) {
-                mask_row = a.mask_base + (((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * 8;
+                mask_row = a.mask_base + (((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * a.mask_words;
                 if (kBwd && j.kind == EK_DMASK) {   // global loads issued now, consumed after the accumulator wait
 #pragma unroll
-                    for (int g = 0; g < 8 / kSplit; ++g) pm[g] = (G0 + g < G1) ? mask_row[G0 + g] : 0u;
+                    for (int g = 0; g < kMaxGroups; ++g) pm[g] = (G0 + g < G1) ? mask_row[G0 + g] : 0u;
                 }
             }
             const unsigned long long te1 = a.trace ? clock64() : 0;
@@ -585,12 +593,15 @@ bool make_lane_program(const TcProgram &p, LaneProgram &out, std::string &err) {
     out = LaneProgram();
     for (size_t i = 0; i < p.ops.size(); ++i) {
         const MmaOp &o = p.ops[i];
-        if (o.flags & TC_OP_FIRST) {
+        if (o.flags & TC_OP_GEMM_START) {
             if (!out.gemms.empty()) out.gemms.back().op_end = (uint16_t)i;
             out.gemms.push_back(LaneGemm{(uint16_t)i, (uint16_t)i});
         }
         if (o.n % 16) { err = "lane program: MMA N must be a multiple of 16 for cta_group::2"; return false; }
-        out.ops.push_back(LaneOp{o.w_off, o.n, o.a_slot, o.kcount});
+        const bool half1 = !(o.flags & TC_OP_GEMM_START) && o.acc == 1 && p.wide;
+        out.ops.push_back(LaneOp{o.w_off, o.n, o.a_slot,
+                                 (uint8_t)(o.kcount | ((o.flags & TC_OP_FIRST) ? LANE_OP_FIRST : 0u) | ((p.wide && o.acc == 1) ? LANE_OP_HALF1 : 0u))});
+        (void)half1;
     }
     if (out.gemms.empty()) { err = "lane program: no GEMMs"; return false; }
     out.gemms.back().op_end = (uint16_t)p.ops.size();
@@ -692,6 +703,7 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
     a.points = l.points; a.rays = l.rays; a.t = l.t; a.poses = l.poses; a.dirs = l.dirs; a.sigma = l.sigma; a.rgba = l.rgba; a.d_sigma = l.d_sigma; a.d_rgba = l.d_rgba;
     a.save_base = l.save_base; a.save_slots = l.save_slots; a.mask_base = l.mask_base; a.mask_slots = l.mask_slots;
     a.trace = l.trace;
+    a.wide = l.wide; a.e_slot = l.e_slot; a.mask_words = l.mask_words;
     const int max_clusters = l.num_sms / 2;
     const int clusters = a.n_pairs < max_clusters ? a.n_pairs : max_clusters;
     const int grid = 2 * clusters;

@@ -28,11 +28,16 @@ struct Builder {
     bool pending[3] = {false, false, false};  // unconsumed "ready" event per slot group
     std::string err;
 
+    bool wide = false;            // hidden 257..512: 8 hidden panels, slot E = 8, N = 512 GEMMs issued as two 256-column halves
+    int e_slot = TC_SLOT_E;
+
     Builder(const NetGeom &g_, TcProgram &p) : g(g_), prog(p) {
         np = g.Wp / 64;
         np2 = g.W2p / 64;
+        wide = np > 4;
+        e_slot = wide ? TC_SLOT_E_WIDE : TC_SLOT_E;
     }
-    static int group_of_slot(int slot) { return slot == TC_SLOT_E ? 2 : slot / 2; }
+    int group_of_slot(int slot) const { return slot == e_slot ? 2 : slot / 2; }
 
     // K-panel input descriptor for one GEMM
     struct KIn {
@@ -45,6 +50,7 @@ struct Builder {
     };
 
     void signal(int slot, EpiJob &j, bool enc) {
+        if (wide) return;   // the per-slot-group ready events are a v1 (one tile per CTA) mechanism; wide runs on the pair kernel only
         const int grp = group_of_slot(slot);
         if (pending[grp]) err = "schedule error: ready event not consumed before the next one";
         pending[grp] = true;
@@ -52,8 +58,10 @@ struct Builder {
         else j.ready_bar = (uint8_t)(TC_BAR_READY + grp);
     }
 
-    // Emit the MMA ops of one GEMM (one op per 64-wide K panel, full N) into accumulator set `acc`.
-    void emit_ops(const std::vector<KIn> &kin, int acc, int n_mma, int valid_rows) {
+    // Emit the MMA ops of one GEMM (or of one 256-column half of a wide GEMM): one op per 64-wide K panel, N = n_mma,
+    // into accumulator set `acc`. row0 = first weight row (output index) of this half.
+    void emit_ops(const std::vector<KIn> &kin, int acc, int n_mma, int valid_rows, int row0 = 0, bool gemm_start = true,
+                  bool commit_last = true) {
         for (size_t i = 0; i < kin.size(); ++i) {
             const KIn &k = kin[i];
             MmaOp op;
@@ -67,19 +75,24 @@ struct Builder {
             op.wait0 = op.wait1 = TC_NONE;
             if (i == 0) {
                 op.flags |= TC_OP_FIRST;
-                op.wait0 = (uint8_t)(TC_BAR_ACC_FREE + acc);
+                if (gemm_start) {
+                    op.flags |= TC_OP_GEMM_START;
+                    op.wait0 = (uint8_t)(TC_BAR_ACC_FREE + acc);
+                }
             }
-            if (i + 1 == kin.size()) op.flags |= TC_OP_COMMIT_ACC;
-            const int grp = group_of_slot(k.slot);
-            if (pending[grp]) {
-                op.wait1 = (uint8_t)(TC_BAR_READY + grp);
-                pending[grp] = false;
+            if (i + 1 == kin.size() && commit_last) op.flags |= TC_OP_COMMIT_ACC;
+            if (!wide) {
+                const int grp = group_of_slot(k.slot);
+                if (pending[grp]) {
+                    op.wait1 = (uint8_t)(TC_BAR_READY + grp);
+                    pending[grp] = false;
+                }
             }
             prog.ops.push_back(op);
             PackChunk pc;
             pc.dst_off = prog.wpack_bytes;
             pc.n_rows = n_mma;
-            pc.src_base = k.src_base;
+            pc.src_base = k.src_base + (int64_t)row0 * k.row_stride;
             pc.row_stride = k.row_stride;
             pc.col_stride = k.col_stride;
             pc.valid_rows = valid_rows < 0 ? 0 : (valid_rows > n_mma ? n_mma : valid_rows);
@@ -112,10 +125,18 @@ struct Builder {
     // that the next GEMM can start on panels 0,1 while block 1 is still being converted.
     void emit_hidden_gemm(const std::vector<KIn> &kin, int n_out_panels, int n_valid, uint8_t kind, uint32_t bias_off,
                           int save_slot0, int mask_slot, uint8_t enc, int enc_save_slot, bool consumed) {
-        const int nblocks = n_out_panels > 2 ? 2 : 1;
-        const int acc = set;
-        set ^= 1;
-        emit_ops(kin, acc, 64 * n_out_panels, n_valid);
+        const int nblocks = (n_out_panels + 1) / 2;
+        int acc = set;
+        if (n_out_panels > 4) {
+            // wide: two 256-column halves sharing the K inputs; the accumulator is TMEM columns [0, 512)
+            acc = 0;
+            emit_ops(kin, 0, 256, n_valid, 0, true, false);
+            emit_ops(kin, 1, 256, n_valid - 256, 256, false, true);
+        } else {
+            if (wide) acc = 0;
+            else set ^= 1;
+            emit_ops(kin, acc, 64 * n_out_panels, n_valid);
+        }
         for (int b = 0; b < nblocks; ++b) {
             const int p0 = 2 * b;
             const int pn = (n_out_panels - p0) > 2 ? 2 : (n_out_panels - p0);
@@ -134,20 +155,20 @@ struct Builder {
             j.mask_slot = (int16_t)mask_slot;
             j.mask_word0 = (uint16_t)(4 * b);
             j.bias_off = (uint16_t)(bias_off + 128u * b);
-            j.acc_col = (uint16_t)(acc * 256 + 128 * b);
+            j.acc_col = (uint16_t)(acc * 256 + 128 * b);   // (wide: acc == 0, blocks 0..3 span both halves)
             if (consumed) signal(j.out_slot, j, false);
             if (b == 0 && enc != ENC_NONE) {
                 j.enc = enc;
                 j.enc_save_slot = (int16_t)enc_save_slot;
-                signal(TC_SLOT_E, j, true);
+                signal(e_slot, j, true);
             }
             prog.jobs.push_back(j);
         }
     }
 
     void emit_small_gemm(const std::vector<KIn> &kin, int valid_rows, uint8_t kind, uint32_t bias_off) {
-        const int acc = set;
-        set ^= 1;
+        const int acc = wide ? 0 : set;
+        if (!wide) set ^= 1;
         emit_ops(kin, acc, 16, valid_rows);
         EpiJob j;
         memset(&j, 0, sizeof(j));
@@ -177,7 +198,7 @@ struct Builder {
         j.save_slot = -1;
         j.mask_slot = -1;
         j.enc_save_slot = (int16_t)enc_save_slot;
-        signal(TC_SLOT_E, j, true);
+        signal(e_slot, j, true);
         prog.jobs.push_back(j);
     }
 };
@@ -204,9 +225,9 @@ struct Slots {
 
 bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     const int npanels = g.Wp / 64;
-    if (g.Wp % 64 || (npanels != 1 && npanels != 2 && npanels != 4) || g.W2p % 64 || g.W2p < 64 || g.W2p > 128 ||
+    if (g.Wp % 64 || (npanels != 1 && npanels != 2 && npanels != 4 && npanels != 8) || g.W2p % 64 || g.W2p < 64 || g.W2p > 256 ||
         g.Cx > 64 || g.Cd > 32) {
-        err = "tcgen05 MLP supports hidden <= 64, <= 128 or 129..256, xyz_freqs <= 10, dir_freqs <= 4";
+        err = "tcgen05 MLP supports hidden <= 64, <= 128, 129..256 or 449..512, xyz_freqs <= 10, dir_freqs <= 4";
         return false;
     }
     if (g.skip_layer && (g.skip_layer < 1 || g.skip_layer > 6)) {
@@ -239,13 +260,14 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     // ---- forward programs (train saves panels + masks, infer does not)
     for (int train = 0; train < 2; ++train) {
         TcProgram &P = train ? plan.fwd_train : plan.fwd_infer;
+        P.wide = np > 4;
         Builder B(g, P);
         B.emit_prologue(EK_PROLOGUE_FWD, ENC_X, train ? sl.X() : -1);
         for (int l = 1; l <= 7; ++l) {
             const LayerGeom &L = g.L[l - 1];
             std::vector<Builder::KIn> kin;
             const bool skip = g.skip_layer && l == g.skip_layer + 1;
-            if (l == 1 || skip) kin.push_back({TC_SLOT_E, 4, L.w_off, L.in_dim, 1, g.Cx});
+            if (l == 1 || skip) kin.push_back({B.e_slot, 4, L.w_off, L.in_dim, 1, g.Cx});
             if (l > 1) B.hidden_kin(kin, np, L.w_off, L.in_dim, 1, skip ? g.Cx : 0, g.W);
             B.emit_hidden_gemm(kin, np, g.W, EK_RELU, bias_l[l], train ? sl.H(l) : -1, train ? (l - 1) : -1, ENC_NONE, -1,
                                true);
@@ -267,7 +289,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
             {   // fc9 on [feat | dir]
                 const LayerGeom &L = g.L[8];
                 std::vector<Builder::KIn> kin;
-                if (g.Cd) kin.push_back({TC_SLOT_E, 2, L.w_off + g.W, L.in_dim, 1, g.Cd});
+                if (g.Cd) kin.push_back({B.e_slot, 2, L.w_off + g.W, L.in_dim, 1, g.Cd});
                 B.hidden_kin(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
                 B.emit_hidden_gemm(kin, np2, g.W2, EK_RELU, bias_9, train ? sl.h9() : -1, train ? 7 : -1, ENC_NONE, -1, true);
             }
@@ -288,6 +310,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     // ---- backward dgrad chain
     {
         TcProgram &P = plan.bwd;
+        P.wide = np > 4;
         Builder B(g, P);
         if (g.use_rgb_head) {
             B.emit_prologue(EK_PROLOGUE_BWD, ENC_NONE, sl.R());
@@ -295,7 +318,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 const LayerGeom &L = g.L[9];
                 std::vector<Builder::KIn> kin;
                 // B chunk rows = in index (h9), cols = out index (4 valid): element = w[(c)*in_dim + r]
-                kin.push_back({TC_SLOT_E, 1, L.w_off, 1, L.in_dim, 4});
+                kin.push_back({B.e_slot, 1, L.w_off, 1, L.in_dim, 4});
                 B.emit_hidden_gemm(kin, np2, g.W2, EK_DMASK, 0, sl.dP9(), 7, ENC_DSIGMA, sl.Sg(), true);
             }
             {   // dFeat = dPre9 * W9[:, 0:W]
@@ -310,7 +333,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
         {   // dH7 = [dsigma | dFeat] * W8 -> mask(h7) -> dPre7
             const LayerGeom &L = g.L[7];
             std::vector<Builder::KIn> kin;
-            kin.push_back({TC_SLOT_E, 1, L.w_off, 1, L.in_dim, 1});
+            kin.push_back({B.e_slot, 1, L.w_off, 1, L.in_dim, 1});
             if (g.use_rgb_head) B.hidden_kin(kin, np, L.w_off + L.in_dim, 1, L.in_dim, 0, g.W);
             B.emit_hidden_gemm(kin, np, g.W, EK_DMASK, 0, sl.dP(7), 6, ENC_NONE, -1, true);
         }
@@ -341,26 +364,43 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
         u.b_base = b_base;
         plan.units.push_back(u);
     };
+    // A layer block [P panels p0..p0+n_p) x [Q panels q0..q0+n_q) is cut into units of at most 4 x 4 panels (TMEM holds a
+    // 256 x 256 fp32 block): hidden <= 256 gives one unit per block, hidden 512 four.
+    auto add_block = [&](int n_p, int p0, int n_q, int q0, int m_valid, int n_valid, int64_t w_base, int row_stride, int64_t b_base) {
+        for (int qa = 0; qa < n_q; qa += 4) {
+            for (int pa = 0; pa < n_p; pa += 4) {
+                const int np_u = n_p - pa < 4 ? n_p - pa : 4, nq_u = n_q - qa < 4 ? n_q - qa : 4;
+                int mv = m_valid - 64 * pa, nv = n_valid - 64 * qa;
+                mv = mv < 0 ? 0 : (mv > 64 * np_u ? 64 * np_u : mv);
+                nv = nv < 0 ? 0 : (nv > 64 * nq_u ? 64 * nq_u : nv);
+                if (mv == 0 || nv == 0) continue;
+                add_unit(np_u, p0 + pa, nq_u, q0 + qa, mv, nv, w_base + (int64_t)(64 * qa) * row_stride + 64 * pa, row_stride,
+                         (b_base >= 0 && pa == 0) ? b_base + 64 * qa : -1);
+            }
+        }
+    };
     for (int l = 1; l <= 7; ++l) {
         const LayerGeom &L = g.L[l - 1];
         const bool skip = g.skip_layer && l == g.skip_layer + 1;
         if (l == 1) {
-            add_unit(1, sl.X(), np, sl.dP(1), g.Cx, g.W, L.w_off, L.in_dim, L.b_off);
+            add_block(1, sl.X(), np, sl.dP(1), g.Cx, g.W, L.w_off, L.in_dim, L.b_off);
         } else {
-            if (skip) add_unit(1, sl.X(), np, sl.dP(l), g.Cx, g.W, L.w_off, L.in_dim, -1);
-            add_unit(np, sl.H(l - 1), np, sl.dP(l), g.W, g.W, L.w_off + (skip ? g.Cx : 0), L.in_dim, L.b_off);
+            if (skip) add_block(1, sl.X(), np, sl.dP(l), g.Cx, g.W, L.w_off, L.in_dim, -1);
+            add_block(np, sl.H(l - 1), np, sl.dP(l), g.W, g.W, L.w_off + (skip ? g.Cx : 0), L.in_dim, L.b_off);
         }
     }
     {
         const LayerGeom &L = g.L[7];
-        add_unit(np, sl.H(7), 1, sl.Sg(), g.W, 1, L.w_off, L.in_dim, L.b_off);  // sigma row
-        if (g.use_rgb_head) add_unit(np, sl.H(7), np, sl.dFeat(), g.W, g.W, L.w_off + L.in_dim, L.in_dim, L.b_off + 1);
+        add_block(np, sl.H(7), 1, sl.Sg(), g.W, 1, L.w_off, L.in_dim, L.b_off);  // sigma row
+        if (g.use_rgb_head) add_block(np, sl.H(7), np, sl.dFeat(), g.W, g.W, L.w_off + L.in_dim, L.in_dim, L.b_off + 1);
     }
     if (g.use_rgb_head) {
         const LayerGeom &L9 = g.L[8], &L10 = g.L[9];
-        add_unit(np, sl.feat(), np2, sl.dP9(), g.W, g.W2, L9.w_off, L9.in_dim, L9.b_off);
-        if (g.Cd) add_unit(1, sl.D(), np2, sl.dP9(), g.Cd, g.W2, L9.w_off + g.W, L9.in_dim, -1);
-        add_unit(np2, sl.h9(), 1, sl.R(), g.W2, 4, L10.w_off, L10.in_dim, L10.b_off);
+        add_block(np, sl.feat(), np2, sl.dP9(), g.W, g.W2, L9.w_off, L9.in_dim, L9.b_off);
+        if (g.Cd) add_block(1, sl.D(), np2, sl.dP9(), g.Cd, g.W2, L9.w_off + g.W, L9.in_dim, -1);
+        add_block(np2, sl.h9(), 1, sl.R(), g.W2, 4, L10.w_off, L10.in_dim, L10.b_off);
     }
+    plan.e_slot = np > 4 ? TC_SLOT_E_WIDE : TC_SLOT_E;
+    plan.mask_words = (np > 4) ? 16 : 8;
     return true;
 }

@@ -83,7 +83,9 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
     inputs. Returns dict(sigma, rgba, act{slot: panel}, grad{slot: panel}, masks{slot: [128,256] bool})."""
     ops, jobs, chunks = plan["ops"], plan["jobs"], plan["chunks"]
     bias = padded_bias(plan, params)
-    slots = np.zeros((NUM_SLOTS, 128, 64), dtype=np.float32)
+    wide = int(ops["a_slot"].max()) > SLOT_E      # hidden 257..512: hidden panels 0..7, encoded inputs in slot 8
+    SLOT_E_ = 8 if wide else SLOT_E
+    slots = np.zeros((9, 128, 64), dtype=np.float32)
     acc = np.zeros((128, 512), dtype=np.float32)   # TMEM columns: two 256-column accumulator sets
     out = dict(sigma=None, rgba=None, saved={}, masks={} if masks is None else masks)
 
@@ -102,7 +104,7 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
                 v = v + bias[j["bias_off"]:j["bias_off"] + nc][None, :]
             if k == EK_RELU:
                 if j["mask_slot"] >= 0:
-                    m = out["masks"].setdefault(int(j["mask_slot"]), np.zeros((128, 256), dtype=bool))
+                    m = out["masks"].setdefault(int(j["mask_slot"]), np.zeros((128, 512), dtype=bool))
                     m[:, 32 * j["mask_word0"]:32 * j["mask_word0"] + nc] = ~np.signbit(v)
                 v = np.maximum(v, 0)
             if k == EK_DMASK:
@@ -119,19 +121,19 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
             out["rgba"] = 1.0 / (1.0 + np.exp(-(acc[:, c0:c0 + 4] + bias[j["bias_off"]:j["bias_off"] + 4][None, :])))
         wrote_e = True
         if k == EK_PROLOGUE_FWD or j["enc"] == ENC_X:
-            slots[SLOT_E] = pad(posenc_x, 64)
+            slots[SLOT_E_] = pad(posenc_x, 64)
         elif j["enc"] == ENC_D:
-            slots[SLOT_E] = pad(posenc_d, 64)
+            slots[SLOT_E_] = pad(posenc_d, 64)
         elif j["enc"] == ENC_DSIGMA:
-            slots[SLOT_E] = 0
-            slots[SLOT_E][:, 0] = d_sigma
+            slots[SLOT_E_] = 0
+            slots[SLOT_E_][:, 0] = d_sigma
         elif k == EK_PROLOGUE_BWD:
-            slots[SLOT_E] = 0
-            slots[SLOT_E][:, :4] = d_rgba * rgba * (1 - rgba)
+            slots[SLOT_E_] = 0
+            slots[SLOT_E_][:, :4] = d_rgba * rgba * (1 - rgba)
         else:
             wrote_e = False
         if wrote_e and j["enc_save_slot"] >= 0:
-            out["saved"][int(j["enc_save_slot"])] = slots[SLOT_E].copy()
+            out["saved"][int(j["enc_save_slot"])] = slots[SLOT_E_].copy()
 
     ji = 0
     while ji < len(jobs) and jobs[ji]["acc"] == NONE:
@@ -148,7 +150,7 @@ def emulate_chain(plan, params, posenc_x, posenc_d, d_sigma=None, d_rgba=None, r
         else:
             acc[:, c0:c0 + n] += prod
         if op["flags"] & OP_COMMIT:
-            assert jobs[ji]["acc"] == op["acc"] and jobs[ji]["flags"] & JOB_WAIT, "job/commit order mismatch"
+            assert (wide or jobs[ji]["acc"] == op["acc"]) and jobs[ji]["flags"] & JOB_WAIT, "job/commit order mismatch"
             while True:   # all jobs of this GEMM, then any prologue-type jobs
                 last = jobs[ji]["flags"] & JOB_RELEASE
                 run_job(jobs[ji]); ji += 1

@@ -18,6 +18,8 @@ CASES = {
     "ns64": dict(hidden=64, num_rays=4, num_samples=50),            # ragged last tile
     "as_shipped": dict(hidden=100, xyz_freqs=0, dir_freqs=-1, skip_layer=0, use_rgb_head=0, num_rays=84, num_samples=64),
     "ns256_big": dict(hidden=256, num_rays=1024, num_samples=64),   # config 0: 512 tiles, > 1 tile per SM
+    "ns512": dict(hidden=512, num_rays=10, num_samples=64),         # BASELINE configs[4] width: 8 panels, single-lane pair kernel, 5 tiles
+    "ns512_big": dict(hidden=512, num_rays=512, num_samples=128),   # 512 tiles
 }
 
 
@@ -60,14 +62,14 @@ def test_tcgen05_predict_matches_oracle(name):
     assert G.rel_err(sig, w_sig.detach().numpy()) < 1e-2
 
 
-@pytest.mark.parametrize("name", ["ns256", "ns128", "as_shipped", "ns256_big"])
+@pytest.mark.parametrize("name", ["ns256", "ns128", "as_shipped", "ns256_big", "ns512", "ns512_big"])
 def test_tcgen05_matches_simt_on_device(name):
     a = _setup(name, _lib.MLP_TCGEN05)
     b = _setup(name, _lib.MLP_SIMT)
     out_a, sig_a = _predict(a[0], a[1], a[4], a[5], a[6])
     out_b, sig_b = _predict(b[0], b[1], b[4], b[5], b[6])
-    # the fused kernel's encoder uses a double-angle recurrence, the SIMT path sincosf: a handful of
-    # bf16 rounding flips in the highest octaves are expected
+    # the fused kernel's encoder uses SFU sin/cos, the SIMT path sincosf: a handful of bf16 rounding flips in the
+    # highest octaves are expected
     assert G.rel_err(sig_a, sig_b) < 8e-3
     assert G.rel_err(out_a, out_b) < 8e-3
 
@@ -81,7 +83,8 @@ def _layer_slices(mcfg):
 
 @pytest.mark.parametrize("name,impl", [("ns64", _lib.MLP_SIMT_FP32), ("ns256", _lib.MLP_SIMT), ("ns64", _lib.MLP_TCGEN05),
                                        ("ns128", _lib.MLP_TCGEN05), ("ns256", _lib.MLP_TCGEN05),
-                                       ("as_shipped", _lib.MLP_TCGEN05), ("ns256_big", _lib.MLP_TCGEN05)])
+                                       ("as_shipped", _lib.MLP_TCGEN05), ("ns256_big", _lib.MLP_TCGEN05),
+                                           ("ns512", _lib.MLP_TCGEN05)])
 def test_step_gradients_loss_and_adam(name, impl):
     m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup(name, impl)
     r, s = cfg.num_rays, cfg.num_samples

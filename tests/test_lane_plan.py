@@ -20,7 +20,7 @@ import pytest
 import nerf_rs_b200 as nb
 from nerf_rs_b200 import _lib
 
-LANE_OP = np.dtype([("w_off", "<u4"), ("n", "<u2"), ("a_slot", "u1"), ("kcount", "u1")])
+LANE_OP = np.dtype([("w_off", "<u4"), ("n", "<u2"), ("a_slot", "u1"), ("kflags", "u1")])   # kflags: K16 steps | 0x40 half 1 | 0x80 first
 LANE_GEMM = np.dtype([("op_begin", "<u2"), ("op_end", "<u2")])
 LANE_JOB = np.dtype([("kind", "u1"), ("enc", "u1"), ("ncols", "<u2"), ("bias_off", "<u2"), ("save_slot", "<i2"),
                      ("enc_save_slot", "<i2"), ("mask_slot", "<i2"), ("out_slot", "u1"), ("pad0", "u1"), ("pad1", "<u2")])
@@ -30,8 +30,8 @@ HIDDEN_KINDS = (1, 2, 6, 7)   # RELU, LINEAR, DMASK, DCOPY
 
 def lane_plan(cfg, program):
     lib = _lib.load()
-    ops, gemms, jobs = np.zeros(64, LANE_OP), np.zeros(32, LANE_GEMM), np.zeros(32, LANE_JOB)
-    n = [ctypes.c_int32(64), ctypes.c_int32(32), ctypes.c_int32(32)]
+    ops, gemms, jobs = np.zeros(256, LANE_OP), np.zeros(32, LANE_GEMM), np.zeros(32, LANE_JOB)
+    n = [ctypes.c_int32(256), ctypes.c_int32(32), ctypes.c_int32(32)]
     rc = lib.nerf_debug_lane_plan(ctypes.byref(cfg), program, ops.ctypes.data, ctypes.byref(n[0]), gemms.ctypes.data,
                                   ctypes.byref(n[1]), jobs.ctypes.data, ctypes.byref(n[2]))
     assert rc == 0, rc
@@ -52,23 +52,27 @@ class Bar:
         return (self.phase & 1) != parity
 
 
-class Sched:   # LaneSched of mlp_tc2.cu
-    def __init__(self, cluster, n_clusters, n_pairs, n_pos):
-        self.p0, self.p1, self.pos, self.stride, self.n_pairs, self.n_pos = cluster, cluster + n_clusters, 0, 2 * n_clusters, n_pairs, n_pos
+class Sched:   # LaneSched of mlp_tc2.cu (wide: one lane walks every pair tile of the cluster)
+    def __init__(self, cluster, n_clusters, n_pairs, n_pos, wide=False):
+        self.p0, self.p1, self.pos, self.n_pairs, self.n_pos, self.wide = cluster, cluster + n_clusters, 0, n_pairs, n_pos, wide
+        self.stride = n_clusters if wide else 2 * n_clusters
 
     def __iter__(self):
         while self.p0 < self.n_pairs:
-            yield self.pos, (2 if self.p1 < self.n_pairs else 1), self.p0, self.p1
+            yield self.pos, (2 if (not self.wide and self.p1 < self.n_pairs) else 1), self.p0, self.p1
             self.pos += 1
             if self.pos == self.n_pos:
                 self.pos = 0
                 self.p0 += self.stride
-                self.p1 += self.stride
+                if not self.wide:
+                    self.p1 += self.stride
 
 
 class Sim:
     def __init__(self, ops, gemms, jobs, n_pairs, n_clusters, save, seed, mutation=None):
         self.ops, self.gemms, self.jobs, self.n_pairs, self.C, self.save = ops, gemms, jobs, n_pairs, n_clusters, save
+        self.wide = any(int(j["ncols"]) > 256 for j in jobs) or int(ops["a_slot"].max()) > 4
+        self.e_slot = 8 if self.wide else SLOT_E
         self.mutation = mutation   # deliberately broken protocol variants: the simulation must reject them
         self.rng = random.Random(seed)
         self.nG = len(gemms)
@@ -82,7 +86,7 @@ class Sim:
         self.save_free = [B(1) for r in range(2)]
         # state: smem contents are version tags
         self.stage = [[None] * K_STAGES for _ in range(2)]            # (w_off)
-        self.slot = [[[None] * 5 for _ in range(2)] for _ in range(2)]  # [cta][lane][slot] = (tile_pair, producing job)
+        self.slot = [[[None] * 9 for _ in range(2)] for _ in range(2)]  # [cta][lane][slot] = (tile_pair, producing job)
         self.acc = [[None, None] for _ in range(2)]                      # [cta][lane] = (pair, gemm) when complete
         self.acc_drained = [[True, True] for _ in range(2)]
         self.inflight = []        # MMAs issued, not yet completed: dicts
@@ -107,7 +111,7 @@ class Sim:
     # ---- roles (generators yield a predicate to wait on)
     def producer(self, cta, relay):
         stage, phase = 0, 0
-        for g, nl, _, _ in Sched(0, self.C, self.n_pairs, self.nG):
+        for g, nl, _, _ in Sched(0, self.C, self.n_pairs, self.nG, self.wide):
             reps = 2 if (nl == 2 and not self.shareable(g)) else 1
             for _ in range(reps):
                 for i in range(int(self.gemms[g]["op_begin"]), int(self.gemms[g]["op_end"])):
@@ -126,7 +130,7 @@ class Sim:
 
     def mma(self):
         stage, phase, done_phase = 0, 0, [0, 0]
-        for g, nl, pr0, pr1 in Sched(0, self.C, self.n_pairs, self.nG):
+        for g, nl, pr0, pr1 in Sched(0, self.C, self.n_pairs, self.nG, self.wide):
             shared = nl == 2 and self.shareable(g)
             stage0, phase0 = stage, phase
             for ln in range(nl):
@@ -173,7 +177,7 @@ class Sim:
         """Index of the job (0 = prologue) whose output GEMM g must find in `slot`."""
         for jg in range(g, -1, -1):   # job jg is the epilogue of GEMM jg-1; jobs 0..g precede GEMM g
             j = self.jobs[jg]
-            if slot == SLOT_E:
+            if slot == self.e_slot:
                 if jg == 0 or int(j["enc"]) != 0:
                     return jg
             elif jg > 0 and int(j["kind"]) in HIDDEN_KINDS and int(j["out_slot"]) <= slot < int(j["out_slot"]) + (int(j["ncols"]) + 63) // 64:
@@ -182,8 +186,8 @@ class Sim:
 
     def epilogue(self, cta, warp):
         aph, sph = [0, 0], [0, 0]
-        stride = 2 * self.C
-        for p, nl, pr0, pr1 in Sched(0, self.C, self.n_pairs, self.nG):
+        stride = self.C if self.wide else 2 * self.C
+        for p, nl, pr0, pr1 in Sched(0, self.C, self.n_pairs, self.nG, self.wide):
             for ln in range(nl):
                 pair = pr1 if ln else pr0
                 first_tile, has_next, last = pair < stride, pair + stride < self.n_pairs, p == self.nG - 1
@@ -200,7 +204,7 @@ class Sim:
                     if self.save:
                         yield lambda: self.save_free[cta][ln].done(sph[ln] ^ 1)
                         sph[ln] ^= 1
-                    write(SLOT_E, (pair, 0))
+                    write(self.e_slot, (pair, 0))
                     signal()
                     if self.save:
                         self.save_ready[cta][ln].arrive()
@@ -209,7 +213,7 @@ class Sim:
                         yield lambda: self.save_free[cta][ln].done(sph[ln] ^ 1)
                     sph[ln] ^= 1
                 if last and has_next:
-                    write(SLOT_E, (pair + stride, 0))
+                    write(self.e_slot, (pair + stride, 0))
                 j = self.jobs[p + 1]
                 yield lambda: self.acc_full[cta][ln].done(aph[ln])
                 aph[ln] ^= 1
@@ -219,7 +223,7 @@ class Sim:
                     for s in range(int(j["out_slot"]), int(j["out_slot"]) + (int(j["ncols"]) + 63) // 64):
                         write(s, (pair, p + 1))
                 if int(j["enc"]) != 0:
-                    write(SLOT_E, (pair, p + 1))
+                    write(self.e_slot, (pair, p + 1))
                 self.drain_count[cta][ln] += 1
                 if self.drain_count[cta][ln] == EPI_WARPS:
                     self.drain_count[cta][ln] = 0
@@ -231,19 +235,19 @@ class Sim:
 
     def store(self, cta):
         rph = [0, 0]
-        stride = 2 * self.C
-        for p, nl, pr0, pr1 in Sched(0, self.C, self.n_pairs, self.nG):
+        stride = self.C if self.wide else 2 * self.C
+        for p, nl, pr0, pr1 in Sched(0, self.C, self.n_pairs, self.nG, self.wide):
             for ln in range(nl):
                 pair = pr1 if ln else pr0
                 steps = []
                 if p == 0 and pair < stride:
-                    steps.append({SLOT_E} if int(self.jobs[0]["enc_save_slot"]) >= 0 else set())
+                    steps.append({self.e_slot} if int(self.jobs[0]["enc_save_slot"]) >= 0 else set())
                 j = self.jobs[p + 1]
                 rd = set()
                 if int(j["save_slot"]) >= 0:
                     rd |= set(range(int(j["out_slot"]), int(j["out_slot"]) + int(j["ncols"]) // 64))
                 if int(j["enc_save_slot"]) >= 0 or (p == self.nG - 1 and pair + stride < self.n_pairs and int(self.jobs[0]["enc_save_slot"]) >= 0):
-                    rd.add(SLOT_E)
+                    rd.add(self.e_slot)
                 steps.append(rd)
                 for rd in steps:
                     yield lambda: self.save_ready[cta][ln].done(rph[ln])
@@ -293,6 +297,7 @@ GEOMS = {
     "ns64": dict(hidden=64),
     "as_shipped": dict(hidden=100, xyz_freqs=0, dir_freqs=-1, skip_layer=0, use_rgb_head=0),
     "noskip_nodir": dict(hidden=256, skip_layer=0, dir_freqs=-1),
+    "ns512": dict(hidden=512),
 }
 
 
@@ -300,16 +305,17 @@ GEOMS = {
 @pytest.mark.parametrize("program", [0, 1, 2])
 def test_lane_program_shape(name, program):
     ops, gemms, jobs = lane_plan(nb.default_config(**GEOMS[name]), program)
-    assert len(jobs) == len(gemms) + 1 and len(ops) <= 48 and len(gemms) <= 16      # kernel-parameter table capacities
+    assert len(jobs) == len(gemms) + 1 and len(ops) <= 160 and len(gemms) <= 16     # kernel-parameter table capacities
     assert int(gemms[0]["op_begin"]) == 0 and int(gemms[-1]["op_end"]) == len(ops)
     assert all(int(a["op_end"]) == int(b["op_begin"]) for a, b in zip(gemms[:-1], gemms[1:]))
-    assert all(int(o["n"]) % 16 == 0 and int(o["n"]) <= 256 and int(o["kcount"]) in (1, 2, 4) for o in ops)   # cta_group::2 shapes
-    assert all(int(j["ncols"]) in (16, 64, 128, 192, 256) for j in jobs[1:])
+    assert all(int(o["n"]) % 16 == 0 and int(o["n"]) <= 256 and (int(o["kflags"]) & 7) in (1, 2, 4) for o in ops)   # cta_group::2 shapes
+    assert all(int(ops[int(gm["op_begin"])]["kflags"]) & 0x80 for gm in gemms)        # every GEMM starts by overwriting its accumulator
+    assert all(int(j["ncols"]) in (16, 64, 128, 192, 256, 512) for j in jobs[1:])
     if program != 1:   # training programs save every hidden panel they produce
         assert all(int(j["save_slot"]) >= 0 for j in jobs[1:] if int(j["kind"]) in HIDDEN_KINDS)
 
 
-@pytest.mark.parametrize("name", ["ns256", "ns64", "as_shipped"])
+@pytest.mark.parametrize("name", ["ns256", "ns64", "as_shipped", "ns512"])
 @pytest.mark.parametrize("program", [0, 1, 2])
 @pytest.mark.parametrize("n_pairs,n_clusters", [(1, 1), (2, 1), (3, 1), (5, 2), (4, 1)])
 def test_protocol_random_interleavings(name, program, n_pairs, n_clusters):

@@ -34,9 +34,12 @@ def _mcfg(over):
                          use_rgb_head=bool(d["use_rgb_head"]))
 
 
-@pytest.mark.parametrize("name", list(CONFIGS))
+WIDE = {"ns512": dict(hidden=512), "ns480_noskip": dict(hidden=480, skip_layer=0)}   # pair kernel only (8 hidden panels)
+
+
+@pytest.mark.parametrize("name", list(CONFIGS) + list(WIDE))
 def test_program_numerics_match_oracle(name):
-    over = CONFIGS[name]
+    over = CONFIGS[name] if name in CONFIGS else WIDE[name]
     cfg = nb.default_config(**over)
     mcfg = _mcfg(over)
     fwd = U.get_plan(cfg, 0)
@@ -107,6 +110,7 @@ def test_chunk_stream_is_contiguous_and_bounded():
 
 
 def test_unsupported_geometry_is_rejected():
-    cfg = nb.default_config(hidden=512)
-    with pytest.raises(nb.NerfError):
-        U.get_plan(cfg, 0)
+    for hidden in (300, 576):      # 5 and 9 panels: neither the 4-panel nor the 8-panel layout
+        cfg = nb.default_config(hidden=hidden)
+        with pytest.raises(nb.NerfError):
+            U.get_plan(cfg, 0)

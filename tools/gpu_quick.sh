@@ -1,10 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python -m pytest tests/test_golden.py -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "golden exit $rc"; tail -n 4 gpurun_out/pytest_gpu.log
+timeout 180 python -m pytest tests/test_gpu_mlp.py -q -m gpu -x -k "ns512" > gpurun_out/pytest_512.log 2>&1; rc=$?; echo "ns512 exit $rc"; tail -n 12 gpurun_out/pytest_512.log
 [ $rc -ne 0 ] && exit 1
 timeout 600 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"; tail -n 6 gpurun_out/pytest_gpu.log
-timeout 200 python tools/trace_chain2.py > gpurun_out/trace2.log 2>&1; echo "trace exit $?"; grep -n "===\|epilogue span\|MMA thread\|producer\|D-encode" gpurun_out/trace2.log
-for i in 1 2; do timeout 200 python bench.py --steps 200 --warmup 5 --no-cpu 2>/dev/null | python -c "
+for i in 1; do timeout 200 python bench.py --steps 200 --warmup 5 --no-cpu 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     if l.startswith('{'):
