@@ -33,12 +33,19 @@ sys.path.insert(0, ROOT)
 IMG = 800
 R, S, W = 4096, 64, 256
 N_VIEW_GRID = 6          # get_view_angles(6) -> 84 (yaw,pitch) pairs, the reference's default
-FWD_FLOP = 2 * 528000    # per sample, W=256
-DGRAD_FLOP = 2 * 492288
-WGRAD_FLOP = 2 * 528000
-# algorithmic (unpadded) HBM bytes per sample, DESIGN.md section 4
-ACT_BYTES = 2 * (63 + 27 + 7 * 256 + 256 + 128)     # bf16 activations saved by the forward (wgrad M-side operand)
-GRAD_BYTES = 2 * (4 + 1 + 128 + 256 + 7 * 256)      # bf16 pre-activation gradients saved by dgrad (wgrad N-side operand)
+CX, CD = 63, 27          # encoded xyz (L=10) and direction (L=4) widths
+
+
+def work_constants(w):
+    """Algorithmic FLOPs and HBM bytes per sample for hidden width w (528 000 / 492 288 MAC at w=256)."""
+    fwd = CX * w + 3 * w * w + (w + CX) * w + 2 * w * w + w * (w + 1) + (w + CD) * (w // 2) + (w // 2) * 4
+    dgrad = fwd - CX * w - CX * w - CD * (w // 2)
+    act = 2 * (CX + CD + 7 * w + w + w // 2)         # bf16 activations saved by the forward (wgrad M-side operand)
+    grad = 2 * (4 + 1 + w // 2 + w + 7 * w)          # bf16 pre-activation gradients saved by dgrad (wgrad N-side operand)
+    return 2 * fwd, 2 * dgrad, 2 * fwd, act, grad
+
+
+FWD_FLOP, DGRAD_FLOP, WGRAD_FLOP, ACT_BYTES, GRAD_BYTES = work_constants(W)
 COMPOSITE_FWD_BYTES, COMPOSITE_BWD_BYTES, SAMPLE_BYTES, ADAM_BYTES_PER_PARAM = 24, 44, 16, 28
 
 
@@ -150,6 +157,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ B200 arm
 def main():
+    global W, FWD_FLOP, DGRAD_FLOP, WGRAD_FLOP, ACT_BYTES, GRAD_BYTES
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -158,6 +166,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--rays", type=int, default=R)
+    ap.add_argument("--hidden", type=int, default=W, help="512 = BASELINE configs[4] width")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -175,6 +184,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     rays, samples = args.rays, args.samples
+    W = args.hidden
+    FWD_FLOP, DGRAD_FLOP, WGRAD_FLOP, ACT_BYTES, GRAD_BYTES = work_constants(W)
     cfg = nb.default_config(image_w=IMG, image_h=IMG, num_rays=rays, num_samples=samples, hidden=W)
     model = nb.NeRF(cfg, device=local)
     angles = nb.get_view_angles(N_VIEW_GRID)
@@ -229,19 +240,22 @@ def main():
     kern = {k: {"ms": v[0] / max(1, v[1]), "launches_per_step": v[1] / prof_steps} for k, v in prof.items()}
     step_prof_ms = sum(v[0] for v in prof.values()) / prof_steps
     n_params = model.num_params
-    # work per launch of each kernel: (bound, algorithmic units) -- FLOP for tensor-bound, bytes for HBM-bound
+    # work per STEP of each kernel: (bound, algorithmic units) -- FLOP for tensor-bound, bytes for HBM-bound. A step that
+    # exceeds the saved-activation budget runs the MLP kernels once per micro-batch (launches_per_step > 1): rates use the
+    # kernel's total time per step.
     work = {
+        "mlp_fwd": ("tensor", FWD_FLOP * nsamp),
         "mlp_fwd_train": ("tensor", FWD_FLOP * nsamp), "mlp_dgrad": ("tensor", DGRAD_FLOP * nsamp),
         "mlp_wgrad": ("hbm", (ACT_BYTES + GRAD_BYTES) * nsamp),
         "sample": ("hbm", SAMPLE_BYTES * nsamp), "composite_fwd": ("hbm", COMPOSITE_FWD_BYTES * nsamp),
         "composite_bwd": ("hbm", COMPOSITE_BWD_BYTES * nsamp), "adam": ("hbm", ADAM_BYTES_PER_PARAM * n_params),
     }
-    traffic = ncu_traffic() if (rays, samples) == (R, S) else {}
+    traffic = ncu_traffic() if (rays, samples, W) == (R, S, 256) else {}
     per_kernel = {}
     for k, (bound, units) in work.items():
         if k not in kern or kern[k]["ms"] <= 0:
             continue
-        sec = kern[k]["ms"] * 1e-3
+        sec = kern[k]["ms"] * 1e-3 * kern[k]["launches_per_step"]
         if bound == "tensor":
             ach, peak, unit = units / sec / 1e12, tf_sus, "TFLOP/s"
         else:
@@ -250,8 +264,8 @@ def main():
                          "share_of_step": kern[k]["ms"] * kern[k]["launches_per_step"] / step_prof_ms,
                          "traffic": traffic.get(k, {}).get("bytes")}
     if "mlp_wgrad" in per_kernel:   # the same kernel against the tensor roof, for reference
-        per_kernel["mlp_wgrad"]["tflops"] = WGRAD_FLOP * nsamp / (kern["mlp_wgrad"]["ms"] * 1e-3) / 1e12
-    mlp_ms = sum(kern[k]["ms"] for k in ("mlp_fwd_train", "mlp_dgrad", "mlp_wgrad") if k in kern)
+        per_kernel["mlp_wgrad"]["tflops"] = WGRAD_FLOP * nsamp / (kern["mlp_wgrad"]["ms"] * kern["mlp_wgrad"]["launches_per_step"] * 1e-3) / 1e12
+    mlp_ms = sum(kern[k]["ms"] * kern[k]["launches_per_step"] for k in ("mlp_fwd", "mlp_fwd_train", "mlp_dgrad", "mlp_wgrad") if k in kern)
     mlp_all = (FWD_FLOP + DGRAD_FLOP + WGRAD_FLOP) * nsamp / (mlp_ms * 1e-3) / 1e12 if mlp_ms > 0 else None
     dom = max(per_kernel, key=lambda k: per_kernel[k]["share_of_step"], default=None)
     roofline = dict(per_kernel[dom]) if dom else {"bound": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
@@ -269,7 +283,7 @@ def main():
     model.profile(False)
     render = None
     if "mlp_fwd" in pr and pr["mlp_fwd"][0] > 0:
-        fwd_ms = pr["mlp_fwd"][0] / pr["mlp_fwd"][1]
+        fwd_ms = pr["mlp_fwd"][0] / 5          # per batch (all micro-batch launches)
         render = {"mlp_fwd_ms": fwd_ms, "mlp_fwd_tflops": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12,
                   "mlp_fwd_frac_of_sustained_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_sus,
                   "mlp_fwd_frac_of_burst_peak": FWD_FLOP * nsamp / (fwd_ms * 1e-3) / 1e12 / tf_burst}

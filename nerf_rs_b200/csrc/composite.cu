@@ -157,7 +157,7 @@ k_composite(CompositeArgs a) {
         __syncthreads();
         if (is_last) {
             float s = 0.f;
-            for (int i = threadIdx.x; i < a.num_rays; i += blockDim.x) s += __ldcg(a.ray_loss + i);
+            for (int i = threadIdx.x; i < a.loss_rays; i += blockDim.x) s += __ldcg(a.loss_rays_first + i);
             sh[threadIdx.x] = s;
             __syncthreads();
             for (int d = (kWarps * 32) >> 1; d > 0; d >>= 1) {

@@ -117,6 +117,7 @@ struct nerf_ctx {
     size_t h_i32_cap = 0;
     bool batch_valid = false, predicted = false, acts_valid = false;
     int gen_pix = 0, gen_view = 0, pick_views = 0;   // Philox picks requested for the next sampler launch
+    bool fwd_deferred = false;            // nerf_train_iter on a micro-batched batch: the forward runs inside nerf_step
     bool points_valid = false;            // d_points holds the batch's sample positions (else: fused sampling in the MLP prologue)
     const ViewPose *batch_poses = nullptr;  // pose table the resident batch's ray records index
 
@@ -323,6 +324,14 @@ int composite_forward(nerf_ctx *c, int nr, float *out) {
 int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool skip_composite = false) {
     if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "predict: no batch (call nerf_get_batch or nerf_predict_points)");
     c->acts_valid = false;
+    c->fwd_deferred = false;
+    if (skip_composite && train && c->chunk < c->R) {
+        // fused iteration over a batch larger than the saved-activation budget: rays are independent, so each micro-batch
+        // runs forward -> compositing backward -> dgrad -> wgrad on its own inside nerf_step; no full forward first
+        c->fwd_deferred = true;
+        c->predicted = true;
+        return NERF_OK;
+    }
     for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
         const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
         const int keep = train && c->chunk >= c->R;
@@ -347,29 +356,40 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         CU(c, cudaMemcpyAsync(c->d_gold, gold, sizeof(float) * 4 * c->R, cudaMemcpyHostToDevice, c->stream));
     }
     const int nranks = c->comm.nranks;
-    {
+    // compositing backward (+ pixels, + fused MSE gradient and loss) of rays [r0, r0+nr); the mean loss over ALL rays is
+    // reduced by the launch that covers the last rays
+    auto composite_backward = [&](int r0, int nr) -> int {
         CompositeArgs a;
         memset(&a, 0, sizeof(a));
-        a.sigma = c->d_sigma;
-        a.colors = c->cfg.use_rgb_head ? c->d_rgba : nullptr;
-        a.t_or_delta = c->d_t;
+        const int64_t s0 = (int64_t)r0 * c->S;
+        a.sigma = c->d_sigma + s0;
+        a.colors = c->cfg.use_rgb_head ? c->d_rgba + 4 * s0 : nullptr;
+        a.t_or_delta = c->d_t + s0;
         a.sigma_relu = c->cfg.sigma_relu;
-        a.num_rays = c->R;
+        a.num_rays = nr;
         a.num_samples = c->S;
-        a.gold = c->d_gold;
+        a.gold = c->d_gold + 4 * (int64_t)r0;
         a.inv_count = 1.f / (4.f * (float)c->R);   // mean over R*4 elements (model.rs:298)
-        a.ray_loss = c->d_ray_loss;
-        a.d_sigma = c->d_dsigma;
-        a.d_colors = c->d_drgba;
-        a.out = c->d_out;                              // the backward pass recomputes the pixels on its way
-        a.loss_out = c->d_loss;                        // ... and the mean loss (model.rs:298), reduced by its last block
-        a.loss_scale = 1.f / (4.f * (float)c->R);
-        a.done_counter = reinterpret_cast<unsigned int *>(c->d_loss + 2);
+        a.ray_loss = c->d_ray_loss + r0;
+        a.d_sigma = c->d_dsigma + s0;
+        a.d_colors = c->d_drgba + 4 * s0;
+        a.out = c->d_out + 4 * (int64_t)r0;            // the backward pass recomputes the pixels on its way
+        if (r0 + nr >= c->R) {                         // ... and the mean loss (model.rs:298), reduced by its last block
+            a.loss_out = c->d_loss;
+            a.loss_rays_first = c->d_ray_loss;
+            a.loss_rays = c->R;
+            a.loss_scale = 1.f / (4.f * (float)c->R);
+            a.done_counter = reinterpret_cast<unsigned int *>(c->d_loss + 2);
+        }
         Scope s(c, "composite_bwd");
         launch_composite_bwd(a, c->num_sms, c->stream);
+        return check_launch(c, "composite_bwd");
+    };
+    int rc = NERF_OK;
+    if (!c->fwd_deferred) {
+        rc = composite_backward(0, c->R);
+        if (rc) return rc;
     }
-    int rc = check_launch(c, "composite_bwd");
-    if (rc) return rc;
     // gradients accumulate (+=) over micro-batches and weight-gradient CTAs: start from zero.
     // With the peer-memory all-reduce the local gradient goes to one of two buffers the other ranks read directly; a
     // buffer is reused two steps later, after every peer has passed the next step's hand-shake.
@@ -379,7 +399,11 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
         const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
         if (!c->acts_valid) {
-            rc = mlp_forward(c, r0, nr, 1);  // recompute this micro-batch's activations
+            rc = mlp_forward(c, r0, nr, 1);  // (re)compute this micro-batch's activations
+            if (rc) return rc;
+        }
+        if (c->fwd_deferred) {
+            rc = composite_backward(r0, nr);
             if (rc) return rc;
         }
         rc = mlp_backward(c, r0, nr, gacc);
@@ -387,6 +411,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     }
     c->acts_valid = false;
     c->predicted = false;
+    c->fwd_deferred = false;
     if (nranks > 1 && !p2p) {
         Scope s(c, "grad_allreduce");
         char eb[256] = {0};

@@ -47,7 +47,9 @@ struct CompositeArgs {
     float *ray_loss;           // [R] per-ray sum of squared errors
     float *d_sigma;            // [R][S]
     float *d_colors;           // [R][S][4]
-    float *loss_out;           // fused mean loss (last block reduces ray_loss in a fixed order), or NULL
+    float *loss_out;           // fused mean loss (last block reduces the per-ray errors in a fixed order), or NULL
+    const float *loss_rays_first;  // first of the loss_rays per-ray errors to reduce (all micro-batches of the step)
+    int32_t loss_rays;
     float loss_scale;          // 1 / (4 R)
     unsigned int *done_counter;  // zero-initialised, reset by the kernel
 };

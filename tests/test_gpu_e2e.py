@@ -134,3 +134,19 @@ def test_render_sharded_single_rank_equals_render():
     assert np.array_equal(full, sh) and np.array_equal(pk, pks)
     part = m.render(0.4, 0.3, 7, 19)                 # an unaligned row band equals the same rows of the full frame
     assert np.array_equal(part, full[7:19])
+
+
+def test_micro_batched_train_iter_equals_single_launch():
+    """nerf_train_iter on a batch larger than the saved-activation budget runs forward -> compositing backward -> dgrad ->
+    wgrad per micro-batch (no full forward first): same loss and the same gradient as the single-launch iteration."""
+    res = []
+    for chunk in (0, 64):
+        cfg = nb.default_config(image_w=64, image_h=64, num_rays=256, num_samples=32, hidden=128, max_rays_per_launch=chunk)
+        m = nb.NeRF(cfg)
+        m.set_weights(M.flatten_params(M.init_params(G.model_cfg(cfg), 0)).numpy())
+        m.set_images(_sphere_images(4, 64, 64))
+        m.set_view_angles(nb.get_view_angles(6)[:4])
+        m.train_iter(7)
+        res.append((m.last_loss(), m.get_grads()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
+    assert np.allclose(res[0][1], res[1][1], rtol=1e-3, atol=1e-6 * np.abs(res[0][1]).max())
