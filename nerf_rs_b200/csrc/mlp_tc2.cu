@@ -220,11 +220,11 @@ __device__ __forceinline__ void store_group(uint32_t lane_base, uint32_t out_slo
 
 // One warp's share of a hidden-layer epilogue: 32-column groups [G0, G1) of the accumulator, one at a time
 // (with four warps per scheduler the other warps cover the TMEM-load and store latencies).
-template <bool kSave, uint8_t kKind>
+template <bool kSave, uint8_t kKind, int kG>
 __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uint32_t lane_base, int bias_base, uint32_t *mask_row,
-                                           uint32_t row, int G0, int G1, const uint32_t (&pm)[kMaxGroups]) {
+                                           uint32_t row, int G0, int G1, const uint32_t (&pm)[kG]) {
 #pragma unroll
-    for (int g = 0; g < kMaxGroups; ++g) {  // unrolled: G stays in the uniform datapath (2 groups per warp; 4 for a 512-column job)
+    for (int g = 0; g < kG; ++g) {  // unrolled: G stays in the uniform datapath (2 groups per warp; 4 for a 512-column job)
         const int G = G0 + g;
         if (G < G1) {
             uint32_t r[32];
@@ -240,8 +240,9 @@ __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uin
     }
 }
 
-template <bool kBwd, bool kSave>
+template <bool kBwd, bool kSave, bool kWide>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain2(const __grid_constant__ Chain2Args a) {
+    constexpr int kG = kWide ? kMaxGroups : kMaxGroups / 2;   // 32-column groups per column-slice warp (256- vs 512-column jobs)
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t bars = sbase + kSmemBars;
@@ -294,7 +295,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         //       GEMM is shareable, once per lane otherwise
         // ===== warp 1 of the peer: relays "my half landed" to the leader's MMA thread, in the same order
         const bool producer = warp == 0;
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, kWide ? 1 : 0);
         uint32_t stage = 0, phase = 0;
         int g, nl, pr0, pr1, ev = 0;
         while (sch.next(g, nl, pr0, pr1)) {
@@ -323,7 +324,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         }
     } else if (warp == 1) {
         // ================= leader: MMA issuer for the pair =================
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, kWide ? 1 : 0);
         uint32_t stage = 0, phase = 0;   // next stage to be consumed for the first time
         uint32_t done_phase = 0;         // bit l: parity to wait for on EPI_DONE[l]
         int mma_ev = 0;
@@ -377,7 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         // ================= store warp (training): bulk-stores every step's panels to the per-tile save area ==========
         // Steps arrive in the epilogue's order. A lane's panels may be rewritten once its stores have finished READING
         // shared memory (SAVE_FREE); the global writes themselves only have to land before the kernel ends.
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, kWide ? 1 : 0);
         uint32_t rph = 0;   // bit l: parity to wait for on SAVE_READY[l]
         const LaneJob pj = s_jobs[0];
         int p, nl, pr0, pr1;
@@ -479,7 +480,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             if (a.trace) ts_b = clock64();
             if (lane_id == 0) ptx::mbar_arrive_cluster(done_bar0 + 8u * (uint32_t)ln);
         };
-        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, a.wide);
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, kWide ? 1 : 0);
         int epi_ev = 0;
         int p, nl, pr0, pr1;
         while (sch.next(p, nl, pr0, pr1)) {
@@ -518,12 +519,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             const int G0 = h * gpw < NG ? h * gpw : NG;
             const int G1 = G0 + gpw < NG ? G0 + gpw : NG;
             uint32_t *mask_row = nullptr;
-            uint32_t pm[kMaxGroups];
+            uint32_t pm[kG];
             if (j.mask_slot >= 0 && j.kind != EK_SIGMA && j.kind != EK_RGBA) {
                 mask_row = a.mask_base + (((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * a.mask_words;
                 if (kBwd && j.kind == EK_DMASK) {   // global loads issued now, consumed after the accumulator wait
 #pragma unroll
-                    for (int g = 0; g < kMaxGroups; ++g) pm[g] = (G0 + g < G1) ? mask_row[G0 + g] : 0u;
+                    for (int g = 0; g < kG; ++g) pm[g] = (G0 + g < G1) ? mask_row[G0 + g] : 0u;
                 }
             }
             const unsigned long long te1 = a.trace ? clock64() : 0;
@@ -534,11 +535,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * 256u;
             if (j.kind == EK_RELU || j.kind == EK_LINEAR || j.kind == EK_DMASK || j.kind == EK_DCOPY) {
                 if (!kBwd) {
-                    if (j.kind == EK_RELU) epi_hidden<kSave, EK_RELU>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
-                    else epi_hidden<kSave, EK_LINEAR>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
+                    if (j.kind == EK_RELU) epi_hidden<kSave, EK_RELU, kG>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
+                    else epi_hidden<kSave, EK_LINEAR, kG>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
                 } else {
-                    if (j.kind == EK_DMASK) epi_hidden<kSave, EK_DMASK>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
-                    else epi_hidden<kSave, EK_DCOPY>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
+                    if (j.kind == EK_DMASK) epi_hidden<kSave, EK_DMASK, kG>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
+                    else epi_hidden<kSave, EK_DCOPY, kG>(j, taddr, lane_base, bias_base, mask_row, row, G0, G1, pm);
                 }
             } else if (j.kind == EK_SIGMA || j.kind == EK_RGBA) {
                 if (h == 0) {
@@ -644,9 +645,12 @@ Lane2Program *tc2_upload(const LaneProgram &p, uint32_t, std::string &err) {
     if (p.ops.size() > (size_t)kMaxOps || p.gemms.size() > (size_t)kMaxGemms) { err = "tc2: program exceeds the kernel-parameter tables"; return nullptr; }
     static bool attr_done = false;
     if (!attr_done) {
-        bool ok = cudaFuncSetAttribute(k_chain2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(k_chain2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(k_chain2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        bool ok = cudaFuncSetAttribute(k_chain2<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         if (!ok) { err = std::string("tc2: cudaFuncSetAttribute failed: ") + cudaGetErrorString(cudaGetLastError()); return nullptr; }
         attr_done = true;
     }
@@ -707,7 +711,13 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
     const int max_clusters = l.num_sms / 2;
     const int clusters = a.n_pairs < max_clusters ? a.n_pairs : max_clusters;
     const int grid = 2 * clusters;
-    if (l.bwd) k_chain2<true, true><<<grid, kThreads, kChain2Smem, st>>>(a);
-    else if (l.save) k_chain2<false, true><<<grid, kThreads, kChain2Smem, st>>>(a);
-    else k_chain2<false, false><<<grid, kThreads, kChain2Smem, st>>>(a);
+    if (l.wide) {
+        if (l.bwd) k_chain2<true, true, true><<<grid, kThreads, kChain2Smem, st>>>(a);
+        else if (l.save) k_chain2<false, true, true><<<grid, kThreads, kChain2Smem, st>>>(a);
+        else k_chain2<false, false, true><<<grid, kThreads, kChain2Smem, st>>>(a);
+    } else {
+        if (l.bwd) k_chain2<true, true, false><<<grid, kThreads, kChain2Smem, st>>>(a);
+        else if (l.save) k_chain2<false, true, false><<<grid, kThreads, kChain2Smem, st>>>(a);
+        else k_chain2<false, false, false><<<grid, kThreads, kChain2Smem, st>>>(a);
+    }
 }
