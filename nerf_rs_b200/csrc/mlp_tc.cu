@@ -18,6 +18,7 @@
 //              range and are flushed once with red.global.add.f32.
 // k_pack       gathers the flat f32 [out,in] parameter blob into the bf16 chunk streams.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -508,7 +509,9 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
             uint32_t stage = 0, phase = 0;
             const uint32_t bytes = (uint32_t)(n_p + n_q) * kWgHalf;
             for (int it = 0; it < n_iters; ++it) {
-                const int tile = wk.tile_begin + (it >> 1);
+                // last tile first: the tail of what the dgrad kernel just wrote is still in L2 (measured -0.6 %; the
+                // TMEM flush at the end costs ~1 us and the 13 units are balanced to 2.4 %: this kernel is HBM-read-bound)
+                const int tile = wk.tile_end - 1 - (it >> 1);
                 const uint32_t half = (uint32_t)(it & 1) * kWgHalf;
                 ptx::mbar_wait(bars + 8 * (kWgStages + stage), phase ^ 1u);
                 ptx::mbar_arrive_expect_tx(bars + 8 * stage, bytes);
