@@ -105,6 +105,12 @@ int nerf_set_adam_state(nerf_ctx *ctx, const float *m, const float *v, int64_t n
  * reference's f32::cos/sin, and the per-view rotation matrices are uploaded. */
 int nerf_set_images(nerf_ctx *ctx, const float *rgba, int32_t n_views);
 int nerf_set_view_angles(nerf_ctx *ctx, const float *yaw_pitch, int32_t n_angles);
+/* The same residency from RGBA8 bytes (what image_loading.rs:6-24 decodes before its `as f32 / 255.`): images stay
+ * 4 bytes per pixel on the device and the sampler's gold gather performs the IEEE division by 255, bit for bit. */
+int nerf_set_images_rgba8(nerf_ctx *ctx, const uint8_t *rgba8, int32_t n_views);
+/* load_image_as_array's decode step (image_loading.rs:7): 8-bit RGBA PNG -> bytes. out may be NULL to query the size;
+ * anything that is not RGBA8 returns NERF_ERR_UNSUPPORTED (the reference produces an empty Vec for it). Host only. */
+int nerf_load_png_rgba8(const char *path, uint8_t *out, int64_t capacity_bytes, int32_t *width, int32_t *height);
 /* get_view_angles restated (image_loading.rs:67-80): writes 2n(n+1) pairs. */
 int nerf_view_angles_grid(int32_t num_views_per_hemisphere, float *yaw_pitch_out, int32_t capacity);
 

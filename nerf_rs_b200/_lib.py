@@ -56,6 +56,8 @@ SIGNATURES = {
     "nerf_get_adam_state": (ctypes.c_int, [vp, vp, vp, i64, P(i64)]),
     "nerf_set_adam_state": (ctypes.c_int, [vp, vp, vp, i64, i64]),
     "nerf_set_images": (ctypes.c_int, [vp, vp, i32]),
+    "nerf_set_images_rgba8": (ctypes.c_int, [vp, vp, i32]),
+    "nerf_load_png_rgba8": (ctypes.c_int, [ctypes.c_char_p, vp, ctypes.c_int64, vp, vp]),
     "nerf_set_view_angles": (ctypes.c_int, [vp, vp, i32]),
     "nerf_view_angles_grid": (ctypes.c_int, [i32, vp, i32]),
     "nerf_get_batch": (ctypes.c_int, [vp, vp, vp, i32, vp, i32, u64, vp, vp, vp, vp, vp]),

@@ -11,6 +11,7 @@ src/main.rs:57-72 (the reference has no plugin interface; these ARE its hot-path
   Trainer.step(predictions, gold, iter)           model.rs:311-325
   get_multiview_batch(model, imgs, view_angles)   dataset.rs:63-139
   NeRF.save / NeRF.load                           model.rs:211-217
+  load_image_as_array / get_image_paths           image_loading.rs:6-54
 
 Where the reference panics (assert_eq!/unwrap), these raise NerfError. Arrays are numpy
 float32/int64 on the HOST, like the Vecs the reference passes; all device work happens
@@ -70,6 +71,28 @@ def get_view_angles(num_views):
     out = np.empty((2 * num_views * (num_views + 1), 2), dtype=np.float32)
     _check(None, _lib.load().nerf_view_angles_grid(num_views, _ptr(out), out.size))
     return out
+
+
+def load_image_rgba8(path):
+    """The decode step of load_image_as_array (image_loading.rs:7): 8-bit RGBA PNG -> uint8 [H, W, 4].
+    Like the reference, anything that is not RGBA8 is refused (it would yield an empty Vec there)."""
+    lib = _lib.load()
+    w, h = ctypes.c_int32(), ctypes.c_int32()
+    _check(None, lib.nerf_load_png_rgba8(str(path).encode(), None, 0, ctypes.byref(w), ctypes.byref(h)))
+    out = np.empty((h.value, w.value, 4), dtype=np.uint8)
+    _check(None, lib.nerf_load_png_rgba8(str(path).encode(), _ptr(out), out.nbytes, ctypes.byref(w), ctypes.byref(h)))
+    return out
+
+
+def load_image_as_array(path):
+    """image_loading.rs:6-24 -> float32 [H*W, 4], each channel `as f32 / 255.`."""
+    return (load_image_rgba8(path).reshape(-1, 4).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+def get_image_paths(directory, start, end, step):
+    """image_loading.rs:37-54: `{dir}/image-{i}.png` for i in (start..end).step_by(step), same asserts."""
+    assert start < end and (end - start) % step == 0 and (end - start) // step > 0
+    return [f"{directory}/image-{i}.png" for i in range(start, end, step)]
 
 
 class NeRF:
@@ -147,6 +170,13 @@ class NeRF:
         assert imgs.ndim == 3 and imgs.shape[1] == self.cfg.image_w * self.cfg.image_h and imgs.shape[2] == 4
         _check(self.h, self.lib.nerf_set_images(self.h, _ptr(imgs), imgs.shape[0]))
         self.n_views = imgs.shape[0]
+
+    def set_images_rgba8(self, imgs_u8):
+        """Residency from RGBA8 bytes [V, H*W, 4] (or [V, H, W, 4]): 4 B/pixel on the device; the gold gather divides by 255."""
+        a = np.ascontiguousarray(imgs_u8, dtype=np.uint8).reshape(len(imgs_u8), -1, 4)
+        assert a.shape[1] == self.cfg.image_w * self.cfg.image_h
+        _check(self.h, self.lib.nerf_set_images_rgba8(self.h, _ptr(a), a.shape[0]))
+        self.n_views = a.shape[0]
 
     def set_view_angles(self, view_angles):
         va = _f32(view_angles)

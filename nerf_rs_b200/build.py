@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnerf_b200.so")
-SOURCES = ["context.cu", "sampling.cu", "composite.cu", "adam.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc_plan.cpp", "comm.cpp"]
+SOURCES = ["context.cu", "sampling.cu", "composite.cu", "adam.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc_plan.cpp", "comm.cpp", "host_io.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v",
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
             f.write(out)
     if failed:
         raise RuntimeError("nvcc build failed")
-    cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
+    cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl", "-lz"]
     subprocess.check_call(cmd)
     return OUT
 

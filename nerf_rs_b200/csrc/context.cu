@@ -98,6 +98,7 @@ struct nerf_ctx {
 
     // dataset
     float *d_images = nullptr;
+    uint8_t *d_images_u8 = nullptr;
     int n_img_views = 0;
     ViewPose *d_poses = nullptr;
     int n_poses = 0;
@@ -482,6 +483,7 @@ int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick
     a.poses = poses;
     a.jitter = jitter;
     a.images = gather_gold ? c->d_images : nullptr;
+    a.images_u8 = gather_gold ? c->d_images_u8 : nullptr;
     a.num_rays = nr;
     a.num_samples = c->S;
     a.img_w = c->cfg.image_w;
@@ -558,7 +560,7 @@ int nerf_destroy(nerf_ctx *c) {
     void *ptrs[] = {c->d_params, c->d_grads, c->d_m, c->d_v, c->d_images, c->d_poses, c->d_render_pose, c->d_pix, c->d_view_pick,
                     c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
                     c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
-                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1]};
+                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1], c->d_images_u8};
     for (void *p : ptrs) cudaFree(p);
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_i32) cudaFreeHost(c->h_i32);
@@ -715,9 +717,25 @@ int nerf_set_images(nerf_ctx *c, const float *rgba, int32_t n_views) {
     if (!c || !rgba || n_views < 1) return NERF_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));
     const size_t bytes = sizeof(float) * 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
-    if (c->d_images) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_images); c->d_images = nullptr; }
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->d_images) { cudaFree(c->d_images); c->d_images = nullptr; }
+    if (c->d_images_u8) { cudaFree(c->d_images_u8); c->d_images_u8 = nullptr; }
     CU(c, cudaMalloc(&c->d_images, bytes));
     CU(c, cudaMemcpyAsync(c->d_images, rgba, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->n_img_views = n_views;
+    return NERF_OK;
+}
+
+int nerf_set_images_rgba8(nerf_ctx *c, const uint8_t *rgba8, int32_t n_views) {
+    if (!c || !rgba8 || n_views < 1) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const size_t bytes = 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (c->d_images) { cudaFree(c->d_images); c->d_images = nullptr; }
+    if (c->d_images_u8) { cudaFree(c->d_images_u8); c->d_images_u8 = nullptr; }
+    CU(c, cudaMalloc(&c->d_images_u8, bytes));
+    CU(c, cudaMemcpyAsync(c->d_images_u8, rgba8, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->n_img_views = n_views;
     return NERF_OK;
@@ -765,7 +783,7 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
     const int R = c->R, S = c->S;
     if (n_picks < 1 || n_picks > R || R % n_picks != 0)
         return fail(c, NERF_ERR_INVALID_ARG, "get_batch: can't divide rays evenly among views (dataset.rs:73-81)");
-    const int n_views = (c->d_images && c->n_img_views < c->n_poses) ? c->n_img_views : c->n_poses;
+    const int n_views = ((c->d_images || c->d_images_u8) && c->n_img_views < c->n_poses) ? c->n_img_views : c->n_poses;
     int rc;
     if (indices_yx) {
         rc = ensure_i32(c, (size_t)2 * R + n_picks);
@@ -796,7 +814,7 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
         dj = c->d_jitter;
     }
     const int64_t ray_base = (int64_t)c->comm.rank * R;
-    rc = run_sampler(c, R, c->d_view_pick, R / n_picks, c->d_poses, 0, dj, randomize, seed, ray_base, c->d_images != nullptr,
+    rc = run_sampler(c, R, c->d_view_pick, R / n_picks, c->d_poses, 0, dj, randomize, seed, ray_base, c->d_images != nullptr || c->d_images_u8 != nullptr,
                      out_points != nullptr);
     if (rc) return rc;
     c->batch_valid = true;
@@ -878,7 +896,7 @@ int nerf_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
 int nerf_train_iter(nerf_ctx *c, uint64_t seed) {
     if (!c) return NERF_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));
-    if (!c->d_images) return fail(c, NERF_ERR_STATE, "train_iter: call nerf_set_images first");
+    if (!c->d_images && !c->d_images_u8) return fail(c, NERF_ERR_STATE, "train_iter: call nerf_set_images first");
     int n_picks = c->n_img_views < c->n_poses ? c->n_img_views : c->n_poses;
     while (n_picks > 1 && c->R % n_picks != 0) --n_picks;   // largest pick count that splits R evenly
     int rc = nerf_get_batch(c, nullptr, nullptr, n_picks, nullptr, 1, seed, nullptr, nullptr, nullptr, nullptr, nullptr);

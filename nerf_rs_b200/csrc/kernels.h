@@ -12,6 +12,7 @@ struct SampleArgs {
     const ViewPose *poses;
     const float *jitter;       // [R][S] or NULL -> Philox
     const float *images;       // [V][H*W][4] or NULL
+    const uint8_t *images_u8;  // [V][H*W][4] RGBA8 (alternative residency): gold = byte / 255
     int32_t num_rays, num_samples, img_w, img_h;
     int32_t randomize, depth_mode;
     float off;                 // tan(FOV/2) * HITHER, from the host

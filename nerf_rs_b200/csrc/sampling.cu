@@ -130,6 +130,8 @@ k_sample(SampleArgs a) {
         }
         if (a.images && lane < 4)  // gold = imgs[n][y*W+x] (dataset.rs:111-114)
             a.gold[4 * (size_t)r + lane] = a.images[(((size_t)view * a.img_h + y) * a.img_w + x) * 4 + lane];
+        else if (a.images_u8 && lane < 4)  // ... with the loader's `as f32 / 255.` (image_loading.rs:13-18) fused in
+            a.gold[4 * (size_t)r + lane] = __fdiv_rn((float)a.images_u8[(((size_t)view * a.img_h + y) * a.img_w + x) * 4 + lane], 255.f);
 
         // ---- points: p = FROM + to*t (:115), then yaw, pitch per point (:128-132)
         for (int base = 0; base < S; base += 32) {
