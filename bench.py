@@ -340,6 +340,9 @@ def main():
 
     if rank != 0:
         return
+    # ---- the HBM-bound stage kernels alone at render-scale sizes (working set > L2): sampling, compositing fwd/bwd, Adam
+    from tools import hbm_stages
+    stages = hbm_stages.run(model, iters=10)
     cpu = None
     if not args.no_cpu:
         v, cms = cpu_reference(10, 1)
@@ -353,7 +356,7 @@ def main():
                    "views": int(n_views), "parallelism": f"dp{world}", "global_rays_per_step": world * rays,
                    "cache": "per-step working set (saved activations + gradients, ~2.4 GB) exceeds the 126 MB L2"},
         "clocks": dict(sampler.summary(), window="timed steps + the per-kernel event pass over the same steps"), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu, "render": render, "final_loss": loss,
+        "cpu_baseline": cpu, "render": render, "hbm_stages": stages, "final_loss": loss,
     }
     print(json.dumps(line))
 

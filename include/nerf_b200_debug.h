@@ -43,6 +43,11 @@ int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slo
  * batch with clock64 tracing of CTA 0. out: [3 roles (MMA issuer, epilogue warp 0, producer)][2048][2]. */
 int nerf_debug_trace(nerf_ctx *ctx, int32_t program, uint64_t *out);
 
+/* Time one HBM-bound stage kernel alone on synthetic device-resident inputs of num_rays x num_samples (sizes above the
+ * 126 MB L2 stream HBM every launch): stage 0 = K-sample writing points + t, 1 = K-composite forward, 2 = K-composite
+ * backward (+ fused MSE gradient and loss), 3 = K-adam over num_rays*num_samples parameters. CUDA events, mean of iters. */
+int nerf_debug_bench_stage(nerf_ctx *ctx, int32_t stage, int32_t num_rays, int32_t num_samples, int32_t iters, float *ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -299,6 +299,14 @@ class NeRF:
     def flush_l2(self):
         _check(self.h, self.lib.nerf_flush_l2(self.h))
 
+    STAGES = {"sample": 0, "composite_fwd": 1, "composite_bwd": 2, "adam": 3}
+
+    def bench_stage(self, stage, num_rays, num_samples, iters=10):
+        """ms per launch of one HBM-bound stage kernel alone on synthetic device-resident inputs (nerf_debug_bench_stage)."""
+        v = ctypes.c_float()
+        _check(self.h, self.lib.nerf_debug_bench_stage(self.h, self.STAGES[stage], num_rays, num_samples, iters, ctypes.byref(v)))
+        return v.value
+
     def debug_read_panel(self, area, tile, slot):
         if area == 2:
             out = np.empty((128, 8), dtype=np.uint32)

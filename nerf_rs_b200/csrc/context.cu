@@ -359,6 +359,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     const int nranks = c->comm.nranks;
     // compositing backward (+ pixels, + fused MSE gradient and loss) of rays [r0, r0+nr); the mean loss over ALL rays is
     // reduced by the launch that covers the last rays
+    int loss_partials_done = 0;   // per-block loss partials written so far this step (d_ray_loss holds up to 2R + 16)
     auto composite_backward = [&](int r0, int nr) -> int {
         CompositeArgs a;
         memset(&a, 0, sizeof(a));
@@ -371,19 +372,19 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         a.num_samples = c->S;
         a.gold = c->d_gold + 4 * (int64_t)r0;
         a.inv_count = 1.f / (4.f * (float)c->R);   // mean over R*4 elements (model.rs:298)
-        a.ray_loss = c->d_ray_loss + r0;
+        a.loss_partials = c->d_ray_loss + loss_partials_done;
+        a.loss_partials_first = c->d_ray_loss;
+        a.loss_partials_prior = loss_partials_done;
         a.d_sigma = c->d_dsigma + s0;
         a.d_colors = c->d_drgba + 4 * s0;
         a.out = c->d_out + 4 * (int64_t)r0;            // the backward pass recomputes the pixels on its way
         if (r0 + nr >= c->R) {                         // ... and the mean loss (model.rs:298), reduced by its last block
             a.loss_out = c->d_loss;
-            a.loss_rays_first = c->d_ray_loss;
-            a.loss_rays = c->R;
             a.loss_scale = 1.f / (4.f * (float)c->R);
             a.done_counter = reinterpret_cast<unsigned int *>(c->d_loss + 2);
         }
         Scope s(c, "composite_bwd");
-        launch_composite_bwd(a, c->num_sms, c->stream);
+        loss_partials_done += launch_composite_bwd(a, c->num_sms, c->stream);
         return check_launch(c, "composite_bwd");
     };
     int rc = NERF_OK;
@@ -640,7 +641,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     CUB(cudaMalloc(&c->d_out, sizeof(float) * 4 * R));
     CUB(cudaMalloc(&c->d_dsigma, sizeof(float) * B));
     CUB(cudaMalloc(&c->d_drgba, sizeof(float) * 4 * B));
-    CUB(cudaMalloc(&c->d_ray_loss, sizeof(float) * R));
+    CUB(cudaMalloc(&c->d_ray_loss, sizeof(float) * (2 * (size_t)R + 16)));   // per-block loss partials: <= ceil(nr/8) per launch
     CUB(cudaMalloc(&c->d_loss, sizeof(float) * 4));
     CUB(cudaMalloc(&c->d_render_pose, sizeof(ViewPose)));
     CUB(cudaMemsetAsync(c->d_gold, 0, sizeof(float) * 4 * R, c->stream));
@@ -1172,6 +1173,111 @@ int nerf_debug_trace(nerf_ctx *c, int32_t program, uint64_t *out) {
                        c->d_sigma, c->d_rgba, (unsigned long long *)out, c->stream))
         return fail(c, NERF_ERR_CUDA, "debug_trace failed");
     return check_launch(c, "debug_trace");
+}
+
+// Stand-alone timing of one HBM-bound stage kernel on synthetic device-resident inputs of `num_rays` x `num_samples`
+// (pick sizes whose working set exceeds the 126 MB L2 so every launch streams HBM). CUDA events on the context's stream.
+int nerf_debug_bench_stage(nerf_ctx *c, int32_t stage, int32_t num_rays, int32_t num_samples, int32_t iters, float *ms_per_launch) {
+    if (!c || !ms_per_launch || num_rays < 1 || num_samples < 1 || num_samples > 256 || iters < 1) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int64_t n = (int64_t)num_rays * num_samples;
+    std::vector<void *> bufs;
+    auto alloc = [&](size_t bytes) -> void * {
+        void *p = nullptr;
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        bufs.push_back(p);
+        return p;
+    };
+    auto release = [&]() { for (void *p : bufs) cudaFree(p); };
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    int rc = NERF_OK;
+    auto timed = [&](auto &&launch) {
+        for (int i = 0; i < 2; ++i) launch(i);
+        cudaEventRecord(e0, c->stream);
+        for (int i = 0; i < iters; ++i) launch(2 + i);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_launch = ms / (float)iters;
+    };
+    if (stage == 0) {   // K-sample writing points + t (16 B/sample), Philox pixels and jitter, reference (sorted) depth mode
+        SampleArgs a;
+        memset(&a, 0, sizeof(a));
+        ViewPose vp;
+        make_pose(0.3f, 0.2f, vp);
+        ViewPose *d_vp = (ViewPose *)alloc(sizeof(vp));
+        a.pix_out = (int32_t *)alloc(sizeof(int32_t) * 2 * (size_t)num_rays);
+        a.rays = (RayRec *)alloc(sizeof(RayRec) * (size_t)num_rays);
+        a.dirs = (float *)alloc(sizeof(float) * 3 * (size_t)num_rays);
+        a.t = (float *)alloc(sizeof(float) * n);
+        a.points = (float *)alloc(sizeof(float) * 3 * n);
+        if (!d_vp || !a.pix_out || !a.rays || !a.dirs || !a.t || !a.points) { release(); return fail(c, NERF_ERR_CUDA, "bench_stage: out of memory"); }
+        cudaMemcpy(d_vp, &vp, sizeof(vp), cudaMemcpyHostToDevice);
+        a.pix_yx = a.pix_out;
+        a.gen_pix = 1;
+        a.rays_per_pick = 1;
+        a.poses = d_vp;
+        a.num_rays = num_rays;
+        a.num_samples = num_samples;
+        a.img_w = c->cfg.image_w;
+        a.img_h = c->cfg.image_h;
+        a.randomize = 1;
+        a.depth_mode = c->cfg.depth_mode;
+        a.off = c->off;
+        timed([&](int i) { a.seed = 77 + i; launch_sample(a, c->num_sms, c->stream); });
+    } else if (stage == 1 || stage == 2) {   // K-composite forward / backward (+ fused MSE gradient and loss)
+        CompositeArgs a;
+        memset(&a, 0, sizeof(a));
+        float *sig = (float *)alloc(sizeof(float) * n), *col = (float *)alloc(sizeof(float) * 4 * n), *dl = (float *)alloc(sizeof(float) * n);
+        float *out = (float *)alloc(sizeof(float) * 4 * (size_t)num_rays), *gold = (float *)alloc(sizeof(float) * 4 * (size_t)num_rays);
+        float *rl = (float *)alloc(sizeof(float) * (size_t)num_rays), *loss = (float *)alloc(sizeof(float) * 4);
+        float *ds = stage == 2 ? (float *)alloc(sizeof(float) * n) : nullptr, *dc = stage == 2 ? (float *)alloc(sizeof(float) * 4 * n) : nullptr;
+        if (!sig || !col || !dl || !out || !gold || !rl || !loss || (stage == 2 && (!ds || !dc))) { release(); return fail(c, NERF_ERR_CUDA, "bench_stage: out of memory"); }
+        launch_fill_uniform(sig, n, 1, 0.f, 4.f, c->stream);
+        launch_fill_uniform(col, 4 * n, 2, 0.f, 1.f, c->stream);
+        launch_fill_uniform(dl, n, 3, 0.f, 2.f / (float)num_samples, c->stream);
+        launch_fill_uniform(gold, 4 * (int64_t)num_rays, 4, 0.f, 1.f, c->stream);
+        cudaMemsetAsync(loss, 0, sizeof(float) * 4, c->stream);
+        a.sigma = sig; a.colors = col; a.t_or_delta = dl;
+        a.input_is_delta = 1;
+        a.sigma_relu = c->cfg.sigma_relu;
+        a.num_rays = num_rays; a.num_samples = num_samples;
+        a.out = out;
+        if (stage == 2) {
+            a.gold = gold;
+            a.inv_count = 1.f / (4.f * (float)num_rays);
+            a.loss_partials = rl; a.d_sigma = ds; a.d_colors = dc;
+            a.loss_out = loss; a.loss_partials_first = rl; a.loss_scale = a.inv_count;
+            a.done_counter = reinterpret_cast<unsigned int *>(loss + 2);
+            timed([&](int) { launch_composite_bwd(a, c->num_sms, c->stream); });
+        } else {
+            timed([&](int) { launch_composite_fwd(a, c->num_sms, c->stream); });
+        }
+    } else if (stage == 3) {   // K-adam over num_rays*num_samples parameters (28 B/param)
+        AdamArgs a;
+        memset(&a, 0, sizeof(a));
+        a.p = (float *)alloc(sizeof(float) * n); a.m = (float *)alloc(sizeof(float) * n);
+        a.v = (float *)alloc(sizeof(float) * n); a.g = (float *)alloc(sizeof(float) * n);
+        if (!a.p || !a.m || !a.v || !a.g) { release(); return fail(c, NERF_ERR_CUDA, "bench_stage: out of memory"); }
+        launch_fill_uniform(a.p, n, 1, -1.f, 1.f, c->stream);
+        launch_fill_uniform(a.g, n, 2, -1.f, 1.f, c->stream);
+        cudaMemsetAsync(a.m, 0, sizeof(float) * n, c->stream);
+        cudaMemsetAsync(a.v, 0, sizeof(float) * n, c->stream);
+        a.n = n;
+        a.lr_over_bc1 = 5e-4f; a.inv_sqrt_bc2 = 1.f; a.beta1 = 0.9f; a.beta2 = 0.999f; a.eps = 1e-8f; a.grad_scale = 1.f;
+        timed([&](int) { launch_adam(a, c->num_sms, c->stream); });
+    } else {
+        rc = fail(c, NERF_ERR_INVALID_ARG, "bench_stage: stage 0 sample, 1 composite fwd, 2 composite bwd, 3 adam");
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    release();
+    if (rc) return rc;
+    return check_launch(c, "bench_stage");
 }
 
 int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3, float *off) {

@@ -45,17 +45,19 @@ struct CompositeArgs {
     const float *gold;         // [R][4] (fused MSE) -- used when d_out == NULL
     const float *d_out;        // [R][4] explicit upstream gradient or NULL
     float inv_count;           // 1 / (4 R_total)
-    float *ray_loss;           // [R] per-ray sum of squared errors
+    float *loss_partials;      // [grid] this launch's per-block sums of squared errors (fused MSE), or NULL
     float *d_sigma;            // [R][S]
     float *d_colors;           // [R][S][4]
     float *loss_out;           // fused mean loss (last block reduces the per-ray errors in a fixed order), or NULL
-    const float *loss_rays_first;  // first of the loss_rays per-ray errors to reduce (all micro-batches of the step)
-    int32_t loss_rays;
+    const float *loss_partials_first;  // first partial of the step (earlier micro-batch launches wrote theirs before this one's)
+    int32_t loss_partials_prior;       // partials written by the step's earlier launches
+    int32_t loss_partials_total;       // prior + this launch's grid (filled in by the launcher)
     float loss_scale;          // 1 / (4 R)
     unsigned int *done_counter;  // zero-initialised, reset by the kernel
 };
 void launch_composite_fwd(const CompositeArgs &a, int num_sms, cudaStream_t st);
-void launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st);
+int launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st);   // returns the grid size (= partials written)
+void launch_fill_uniform(float *p, int64_t n, uint32_t seed, float lo, float hi, cudaStream_t st);   // synthetic inputs for stage timing
 void launch_loss_reduce(const float *ray_loss, int n, float inv_count, float *loss_out, cudaStream_t st);
 
 // ---------------------------------------------------------------- adam.cu

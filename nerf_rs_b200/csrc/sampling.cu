@@ -51,11 +51,46 @@ __global__ void k_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_
 }
 
 constexpr int kWarpsPerBlock = 8;
-constexpr int kMaxS = 256;
 
+// Ascending bitonic sort of 32*SPL floats held one per (register k, lane): element i = 32 k + lane. Partners closer than
+// 32 apart are exchanged with a shuffle, the others are register pairs of the same lane whose direction is a compile-time
+// constant after unrolling -- no shared memory and no barriers (the reference sorts (p,t) pairs by t, ray_sampling.rs:125;
+// t = 2u, so sorting the uniforms is the same order).
+template <int SPL>
+__device__ __forceinline__ void warp_bitonic_sort(float (&v)[SPL], int lane) {
+    constexpr int N = 32 * SPL;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const int l = k ^ (j >> 5);
+                    if (l > k) {
+                        const bool up = (((32 * k) & kk) == 0);
+                        const float lo = fminf(v[k], v[l]), hi = fmaxf(v[k], v[l]);
+                        v[k] = up ? lo : hi;
+                        v[l] = up ? hi : lo;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < SPL; ++k) {
+                    const bool up = (((32 * k + lane) & kk) == 0);
+                    const bool lower = ((lane & j) == 0);
+                    const float o = __shfl_xor_sync(0xffffffffu, v[k], j);
+                    v[k] = (lower == up) ? fminf(v[k], o) : fmaxf(v[k], o);
+                }
+            }
+        }
+    }
+}
+
+// SPL = registers per lane for the ray's depths: the next power of two of ceil(S / 32) (S <= 256).
+template <int SPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_sample(SampleArgs a) {
-    __shared__ float s_t[kWarpsPerBlock][kMaxS];
     __shared__ float s_p[kWarpsPerBlock][96];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = a.num_samples;
@@ -82,41 +117,25 @@ k_sample(SampleArgs a) {
         float to[3];
         screen_to_world((float)x, (float)y, (float)a.img_w, (float)a.img_h, a.off, to);
 
-        // ---- depths (ray_sampling.rs:107-125)
-        float *st = s_t[warp];
-        for (int i = lane; i < S; i += 32) {
-            float t;
-            if (!a.randomize) {
-                t = mul(__fdiv_rn((float)i, (float)S), 2.0f);  // :112,:114
-            } else {
-                const float u = a.jitter ? a.jitter[(size_t)r * S + i]
-                                         : philox_uniform(a.seed, NERF_STREAM_JITTER, (uint64_t)(a.ray_index_base + r) * S + i);
-                if (a.depth_mode == 0) t = mul(u, 2.0f);                                       // :110,:114
-                else t = mul(__fdiv_rn(add((float)i, u), (float)S), 2.0f);                      // stratified
-            }
-            st[i] = t;
-        }
-        __syncwarp();
-        if (a.randomize && a.depth_mode == 0) {
-            // sort ascending by t (:125): bitonic network over the next power of two, +inf padded
-            int n = 32;
-            while (n < S) n <<= 1;
-            for (int i = S + lane; i < n; i += 32) st[i] = __int_as_float(0x7f800000);
-            __syncwarp();
-            for (int k = 2; k <= n; k <<= 1) {
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = lane; i < n; i += 32) {
-                        const int l = i ^ j;
-                        if (l > i) {
-                            const float v0 = st[i], v1 = st[l];
-                            const bool up = ((i & k) == 0);
-                            if ((v0 > v1) == up) { st[i] = v1; st[l] = v0; }
-                        }
-                    }
-                    __syncwarp();
+        // ---- depths (ray_sampling.rs:107-125): sample i = 32 k + lane lives in tv[k]
+        float tv[SPL];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int i = 32 * k + lane;
+            float t = __int_as_float(0x7f800000);   // +inf padding sorts to the end
+            if (i < S) {
+                if (!a.randomize) {
+                    t = mul(__fdiv_rn((float)i, (float)S), 2.0f);  // :112,:114
+                } else {
+                    const float u = a.jitter ? a.jitter[(size_t)r * S + i]
+                                             : philox_uniform(a.seed, NERF_STREAM_JITTER, (uint64_t)(a.ray_index_base + r) * S + i);
+                    if (a.depth_mode == 0) t = mul(u, 2.0f);                                       // :110,:114
+                    else t = mul(__fdiv_rn(add((float)i, u), (float)S), 2.0f);                      // stratified
                 }
             }
+            tv[k] = t;
         }
+        if (a.randomize && a.depth_mode == 0) warp_bitonic_sort<SPL>(tv, lane);   // sort ascending by t (:125)
 
         // ---- per-ray outputs
         if (lane == 0) {
@@ -134,22 +153,25 @@ k_sample(SampleArgs a) {
             a.gold[4 * (size_t)r + lane] = __fdiv_rn((float)a.images_u8[(((size_t)view * a.img_h + y) * a.img_w + x) * 4 + lane], 255.f);
 
         // ---- points: p = FROM + to*t (:115), then yaw, pitch per point (:128-132)
-        for (int base = 0; base < S; base += 32) {
-            const int i = base + lane;
-            if (i < S) {
-                const float t = st[i];
-                a.t[(size_t)r * S + i] = t;
-                float q[3];
-                raygeom::sample_point(vp, to, t, q);
-                s_p[warp][3 * lane] = q[0]; s_p[warp][3 * lane + 1] = q[1]; s_p[warp][3 * lane + 2] = q[2];
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int base = 32 * k;
+            if (base < S) {   // warp-uniform
+                const int i = base + lane;
+                if (i < S) a.t[(size_t)r * S + i] = tv[k];
+                if (a.points) {
+                    if (i < S) {
+                        float q[3];
+                        raygeom::sample_point(vp, to, tv[k], q);
+                        s_p[warp][3 * lane] = q[0]; s_p[warp][3 * lane + 1] = q[1]; s_p[warp][3 * lane + 2] = q[2];
+                    }
+                    __syncwarp();
+                    const int nvalid = min(32, S - base) * 3;
+                    float *dst = a.points + ((size_t)r * S + base) * 3;
+                    for (int q = lane; q < nvalid; q += 32) dst[q] = s_p[warp][q];
+                    __syncwarp();
+                }
             }
-            __syncwarp();
-            if (a.points) {
-                const int nvalid = min(32, S - base) * 3;
-                float *dst = a.points + ((size_t)r * S + base) * 3;
-                for (int k = lane; k < nvalid; k += 32) dst[k] = s_p[warp][k];
-            }
-            __syncwarp();
         }
     }
 }
@@ -216,12 +238,22 @@ void launch_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks,
                                             gen_view);
 }
 
-void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st) {
+template <int SPL>
+static void launch_sample_spl(const SampleArgs &a, int num_sms, cudaStream_t st) {
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_sample<SPL>, kWarpsPerBlock * 32, 0);
     int blocks = (a.num_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    int cap = num_sms * 8;
+    const int cap = num_sms * (occ < 1 ? 1 : occ);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k_sample<<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    k_sample<SPL><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+}
+void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st) {
+    const int spl = (a.num_samples + 31) / 32;
+    if (spl <= 1) launch_sample_spl<1>(a, num_sms, st);
+    else if (spl <= 2) launch_sample_spl<2>(a, num_sms, st);
+    else if (spl <= 4) launch_sample_spl<4>(a, num_sms, st);
+    else launch_sample_spl<8>(a, num_sms, st);
 }
 
 void launch_encode(const float *x, float *out, int64_t n, int freqs, int repeat, cudaStream_t st) {
