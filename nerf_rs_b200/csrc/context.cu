@@ -1280,6 +1280,14 @@ int nerf_debug_bench_stage(nerf_ctx *c, int32_t stage, int32_t num_rays, int32_t
     return check_launch(c, "bench_stage");
 }
 
+int nerf_debug_wgrad_marks(nerf_ctx *c, uint64_t *out, int32_t capacity_ctas) {
+    if (!c || !out || !c->tc) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    const int n = tc_debug_wgrad_marks(c->tc, reinterpret_cast<unsigned long long *>(out), capacity_ctas, c->stream);
+    if (n < 0) return fail(c, NERF_ERR_INVALID_ARG, "wgrad_marks: capacity too small or copy failed");
+    return n;
+}
+
 int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3, float *off) {
     ViewPose vp;
     make_pose(yaw, pitch, vp);

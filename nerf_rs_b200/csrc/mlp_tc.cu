@@ -473,6 +473,14 @@ struct WgradArgs {
     float *grads;
 };
 
+// per-CTA wall-clock marks of the last k_wgrad launch (ns, %globaltimer): start, first stage landed, all MMAs done, end
+__device__ unsigned long long g_wgrad_marks[256 * 4];
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = ptx::smem_u32(smem);
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     float *s_bias = reinterpret_cast<float *>(smem + kWgBars + 80);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const WgradWork wk = a.work[blockIdx.x];
+    if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x] = global_ns();
     if (wk.tile_begin >= wk.tile_end) return;  // uniform per CTA
     const WgradUnit u = a.units[wk.unit];
     const int n_p = u.n_p, n_q = u.n_q;
@@ -559,6 +568,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
         uint32_t stage = 0, phase = 0;
         for (int it = 0; it < n_iters; ++it) {
             ptx::mbar_wait(bars + 8 * stage, phase);
+            if (it == 0 && tid == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 1] = global_ns();
             if (has_bias) {
                 const uint32_t qaddr = sbase + stage * kWgStageBytes + (uint32_t)(n_p + (c8 >> 3)) * kWgHalf;
                 for (int rr = 0; rr < rpr; ++rr) {
@@ -588,18 +598,22 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
         // flush the TMEM-resident dW^T block: lane = input index (contiguous in dW rows -> coalesced REDs)
         ptx::mbar_wait(bars + 8 * (2 * kWgStages), 0);
         ptx::tc_fence_after();
-        for (int mb = 0; mb < mblocks; ++mb) {
+        if (tid == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 2] = global_ns();
+        // the CTAs of a unit finish together and add into the same dW block: each starts at a different (M block, column
+        // group) so they do not queue on the same L2 lines
+        const int n_groups = N >> 5, n_pairs = mblocks * n_groups;
+        for (int pi = 0; pi < n_pairs; ++pi) {
+            const int pr = (pi + (int)blockIdx.x) % n_pairs;
+            const int mb = pr / n_groups, g = pr % n_groups;
             const int m = mb * 128 + (int)(q * 32) + lane;
-            for (int g = 0; g < (N >> 5); ++g) {
-                uint32_t r[32];
-                ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)g * 32u, r);
-                ptx::tmem_ld_wait();
-                if (m < u.m_valid) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)g * 32u, r);
+            ptx::tmem_ld_wait();
+            if (m < u.m_valid) {
 #pragma unroll
-                    for (int jn = 0; jn < 32; ++jn) {
-                        const int n = g * 32 + jn;
-                        if (n < u.n_valid) atomicAdd(a.grads + u.w_base + (int64_t)n * u.w_row_stride + m, __uint_as_float(r[jn]));
-                    }
+                for (int jn = 0; jn < 32; ++jn) {
+                    const int n = g * 32 + jn;
+                    if (n < u.n_valid) atomicAdd(a.grads + u.w_base + (int64_t)n * u.w_row_stride + m, __uint_as_float(r[jn]));
                 }
             }
         }
@@ -607,6 +621,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
+    if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 3] = global_ns();
 }
 
 // ---------------------------------------------------------------------------------- pack
@@ -858,7 +873,14 @@ static void build_work(TcState *s, int64_t n_tiles, cudaStream_t st) {
     const int U = (int)s->plan.units.size();
     std::vector<int> cost(U), cnt(U);
     int total = 0;
-    for (int i = 0; i < U; ++i) { cost[i] = s->plan.units[i].n_p + s->plan.units[i].n_q; total += cost[i]; }
+    // measured per half-tile iteration (tools/wgrad_marks.py): 0.42 us + 0.10 us per 8 KB half panel -- a ring stage costs a
+    // fixed latency on top of its bytes, so small units need more CTAs than their byte share
+    // (+ ~0.08 us when a one-M-block unit also sums biases: its epilogue pass outlasts its four MMAs). Costs in 0.01 us.
+    for (int i = 0; i < U; ++i) {
+        const WgradUnit &u = s->plan.units[i];
+        cost[i] = 10 * (u.n_p + u.n_q) + 40 + ((u.b_base >= 0 && u.n_p <= 2 && u.n_q >= 4) ? 8 : 0);
+        total += cost[i];
+    }
     int used = 0;
     for (int i = 0; i < U; ++i) {
         int c = (int)((int64_t)G * cost[i] / total);
@@ -955,6 +977,27 @@ int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaS
     if (!src) return -1;
     if (cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
     return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -2;
+}
+
+// marks of the last k_wgrad launch + the CTA -> (unit, tile range) assignment; out: [num_sms][8] = start, first stage, MMAs
+// done, end (ns), unit, tile_begin, tile_end, n_p + n_q
+int tc_debug_wgrad_marks(TcState *s, unsigned long long *out, int capacity_ctas, cudaStream_t st) {
+    cudaStreamSynchronize(st);
+    const int G = s->num_sms < 256 ? s->num_sms : 256;
+    if (capacity_ctas < G) return -1;
+    std::vector<unsigned long long> marks((size_t)G * 4);
+    if (cudaMemcpyFromSymbol(marks.data(), g_wgrad_marks, sizeof(unsigned long long) * 4 * G) != cudaSuccess) return -2;
+    std::vector<WgradWork> work((size_t)G);
+    if (cudaMemcpy(work.data(), s->d_work, sizeof(WgradWork) * G, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
+    for (int i = 0; i < G; ++i) {
+        for (int k = 0; k < 4; ++k) out[8 * i + k] = marks[4 * i + k];
+        out[8 * i + 4] = (unsigned long long)work[i].unit;
+        out[8 * i + 5] = (unsigned long long)work[i].tile_begin;
+        out[8 * i + 6] = (unsigned long long)work[i].tile_end;
+        const WgradUnit &u = s->plan.units[work[i].unit];
+        out[8 * i + 7] = (unsigned long long)(u.n_p + u.n_q);
+    }
+    return G;
 }
 
 int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n, int S, int program, const float *rgba,
