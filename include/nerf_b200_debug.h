@@ -44,7 +44,7 @@ int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slo
 int nerf_debug_trace(nerf_ctx *ctx, int32_t program, uint64_t *out);
 
 /* Per-CTA wall-clock marks of the last weight-gradient launch: out[cta][8] = start, first ring stage landed, all MMAs
- * done, end (ns, %globaltimer), unit, tile_begin, tile_end, panels per half tile. Returns the CTA count (>= 0) or an error. */
+ * done, end (ns, %globaltimer), first unit, segments, half-tile iterations, bytes loaded. Returns the CTA count (>= 0) or an error. */
 int nerf_debug_wgrad_marks(nerf_ctx *ctx, uint64_t *out, int32_t capacity_ctas);
 
 /* Time one HBM-bound stage kernel alone on synthetic device-resident inputs of num_rays x num_samples (sizes above the

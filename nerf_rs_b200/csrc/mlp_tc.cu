@@ -490,12 +490,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const WgradWork wk = a.work[blockIdx.x];
     if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x] = global_ns();
-    if (wk.tile_begin >= wk.tile_end) return;  // uniform per CTA
-    const WgradUnit u = a.units[wk.unit];
-    const int n_p = u.n_p, n_q = u.n_q;
-    const int N = 64 * n_q;
-    const int mblocks = (n_p + 1) >> 1;
-    const int n_iters = (wk.tile_end - wk.tile_begin) * 2;
+    if (wk.n_seg <= 0) return;  // uniform per CTA
 
     if (threadIdx.x == 0) {
         if (sbase & 1023u) __trap();
@@ -506,120 +501,134 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
         ptx::mbar_init(bars + 8 * (2 * kWgStages), 1);
         ptx::fence_mbar_init();
     }
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = 0.f;
     if (warp == 2) ptx::tmem_alloc<512>(ptx::smem_u32(const_cast<uint32_t *>(tmem_ptr_smem)));
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint32_t bytes = (uint32_t)(n_p + n_q) * kWgHalf;
-            for (int it = 0; it < n_iters; ++it) {
-                // last tile first: the tail of what the dgrad kernel just wrote is still in L2 (measured -0.6 %; the
-                // TMEM flush at the end costs ~1 us and the 13 units are balanced to 2.4 %: this kernel is HBM-read-bound)
-                const int tile = wk.tile_end - 1 - (it >> 1);
-                const uint32_t half = (uint32_t)(it & 1) * kWgHalf;
-                ptx::mbar_wait(bars + 8 * (kWgStages + stage), phase ^ 1u);
-                ptx::mbar_arrive_expect_tx(bars + 8 * stage, bytes);
-                const uint32_t dst = sbase + stage * kWgStageBytes;
-                const uint8_t *ab = a.act_base + (size_t)tile * a.act_slots * kSlotBytes + half;
-                const uint8_t *gb = a.grad_base + (size_t)tile * a.grad_slots * kSlotBytes + half;
-                for (int i = 0; i < n_p; ++i)
-                    ptx::bulk_g2s(dst + i * kWgHalf, ab + (size_t)u.p_slot[i] * kSlotBytes, kWgHalf, bars + 8 * stage);
-                for (int i = 0; i < n_q; ++i)
-                    ptx::bulk_g2s(dst + (n_p + i) * kWgHalf, gb + (size_t)u.q_slot[i] * kSlotBytes, kWgHalf, bars + 8 * stage);
-                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+    // A CTA works through up to kWgMaxSeg segments = (unit, tile range) pieces, so the 148 CTAs can split the units' total
+    // cost evenly instead of in whole CTAs per unit. Ring stage / phase counters simply run on across segments (every role
+    // performs the same number of iterations); the accumulator is flushed and the CTA re-synchronised between segments.
+    uint32_t stage = 0, phase = 0;   // per-thread copies; advanced identically by the producer, MMA and epilogue threads
+    for (int seg = 0; seg < wk.n_seg; ++seg) {
+        const WgradUnit u = a.units[wk.seg[seg].unit];
+        const int tile_end = wk.seg[seg].tile_end;
+        const int n_p = u.n_p, n_q = u.n_q;
+        const int N = 64 * n_q;
+        const int mblocks = (n_p + 1) >> 1;
+        const int n_iters = (tile_end - wk.seg[seg].tile_begin) * 2;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = 0.f;
+        __syncthreads();
+
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(n_p + n_q) * kWgHalf;
+                for (int it = 0; it < n_iters; ++it) {
+                    // last tile first: the tail of what the dgrad kernel just wrote is still in L2
+                    const int tile = tile_end - 1 - (it >> 1);
+                    const uint32_t half = (uint32_t)(it & 1) * kWgHalf;
+                    ptx::mbar_wait(bars + 8 * (kWgStages + stage), phase ^ 1u);
+                    ptx::mbar_arrive_expect_tx(bars + 8 * stage, bytes);
+                    const uint32_t dst = sbase + stage * kWgStageBytes;
+                    const uint8_t *ab = a.act_base + (size_t)tile * a.act_slots * kSlotBytes + half;
+                    const uint8_t *gb = a.grad_base + (size_t)tile * a.grad_slots * kSlotBytes + half;
+                    for (int i = 0; i < n_p; ++i)
+                        ptx::bulk_g2s(dst + i * kWgHalf, ab + (size_t)u.p_slot[i] * kSlotBytes, kWgHalf, bars + 8 * stage);
+                    for (int i = 0; i < n_q; ++i)
+                        ptx::bulk_g2s(dst + (n_p + i) * kWgHalf, gb + (size_t)u.q_slot[i] * kSlotBytes, kWgHalf, bars + 8 * stage);
+                    if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+                }
             }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)N, 1, 1);
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)N, 1, 1);
+                for (int it = 0; it < n_iters; ++it) {
+                    ptx::mbar_wait(bars + 8 * stage, phase);
+                    ptx::tc_fence_after();
+                    const uint32_t st_addr = sbase + stage * kWgStageBytes;
+                    for (int mb = 0; mb < mblocks; ++mb) {
+                        for (uint32_t k = 0; k < 4; ++k) {
+                            // 16 sample rows per K step = 2048 B; 64-element M/N blocks are kWgHalf apart
+                            const uint64_t ad = ptx::umma_desc_sw128(st_addr + (uint32_t)(2 * mb) * kWgHalf + k * 2048u, kWgHalf, 1024);
+                            const uint64_t bd = ptx::umma_desc_sw128(st_addr + (uint32_t)n_p * kWgHalf + k * 2048u, kWgHalf, 1024);
+                            ptx::umma_ss(tmem_base + (uint32_t)mb * 256u, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    ptx::umma_commit(bars + 8 * (kWgStages + stage));
+                    if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+                }
+                ptx::umma_commit(bars + 8 * (2 * kWgStages));
+            }
+        } else if (warp >= 4) {
+            const int tid = threadIdx.x - 128;
+            const bool has_bias = u.b_base >= 0;
+            const int ccols = N >> 3;            // 16-byte chunk columns of Q
+            const int c8 = tid % ccols;
+            const int rg = tid / ccols;
+            const int n_rg = kEpiThreads / ccols;
+            const int rpr = 64 / n_rg;           // rows per row group per half tile
+            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             for (int it = 0; it < n_iters; ++it) {
                 ptx::mbar_wait(bars + 8 * stage, phase);
-                ptx::tc_fence_after();
-                const uint32_t st_addr = sbase + stage * kWgStageBytes;
-                for (int mb = 0; mb < mblocks; ++mb) {
-                    for (uint32_t k = 0; k < 4; ++k) {
-                        // 16 sample rows per K step = 2048 B; 64-element M/N blocks are kWgHalf apart
-                        const uint64_t ad = ptx::umma_desc_sw128(st_addr + (uint32_t)(2 * mb) * kWgHalf + k * 2048u, kWgHalf, 1024);
-                        const uint64_t bd = ptx::umma_desc_sw128(st_addr + (uint32_t)n_p * kWgHalf + k * 2048u, kWgHalf, 1024);
-                        ptx::umma_ss(tmem_base + (uint32_t)mb * 256u, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                if (seg == 0 && it == 0 && tid == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 1] = global_ns();
+                if (has_bias) {
+                    const uint32_t qaddr = sbase + stage * kWgStageBytes + (uint32_t)(n_p + (c8 >> 3)) * kWgHalf;
+                    for (int rr = 0; rr < rpr; ++rr) {
+                        const uint32_t r = (uint32_t)(rg * rpr + rr);
+                        uint32_t w0, w1, w2, w3;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                     : "r"(panel_chunk_addr(qaddr, r, (uint32_t)(c8 & 7))));
+                        bsum[0] += __uint_as_float(w0 << 16); bsum[1] += __uint_as_float(w0 & 0xffff0000u);
+                        bsum[2] += __uint_as_float(w1 << 16); bsum[3] += __uint_as_float(w1 & 0xffff0000u);
+                        bsum[4] += __uint_as_float(w2 << 16); bsum[5] += __uint_as_float(w2 & 0xffff0000u);
+                        bsum[6] += __uint_as_float(w3 << 16); bsum[7] += __uint_as_float(w3 & 0xffff0000u);
                     }
                 }
-                ptx::umma_commit(bars + 8 * (kWgStages + stage));
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bars + 8 * (kWgStages + stage));
                 if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
             }
-            ptx::umma_commit(bars + 8 * (2 * kWgStages));
-        }
-    } else if (warp >= 4) {
-        const uint32_t q = (uint32_t)(warp - 4);
-        const int tid = threadIdx.x - 128;
-        const bool has_bias = u.b_base >= 0;
-        const int ccols = N >> 3;            // 16-byte chunk columns of Q
-        const int c8 = tid % ccols;
-        const int rg = tid / ccols;
-        const int n_rg = kEpiThreads / ccols;
-        const int rpr = 64 / n_rg;           // rows per row group per half tile
-        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        uint32_t stage = 0, phase = 0;
-        for (int it = 0; it < n_iters; ++it) {
-            ptx::mbar_wait(bars + 8 * stage, phase);
-            if (it == 0 && tid == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 1] = global_ns();
             if (has_bias) {
-                const uint32_t qaddr = sbase + stage * kWgStageBytes + (uint32_t)(n_p + (c8 >> 3)) * kWgHalf;
-                for (int rr = 0; rr < rpr; ++rr) {
-                    const uint32_t r = (uint32_t)(rg * rpr + rr);
-                    uint32_t w0, w1, w2, w3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
-                                 : "r"(panel_chunk_addr(qaddr, r, (uint32_t)(c8 & 7))));
-                    bsum[0] += __uint_as_float(w0 << 16); bsum[1] += __uint_as_float(w0 & 0xffff0000u);
-                    bsum[2] += __uint_as_float(w1 << 16); bsum[3] += __uint_as_float(w1 & 0xffff0000u);
-                    bsum[4] += __uint_as_float(w2 << 16); bsum[5] += __uint_as_float(w2 & 0xffff0000u);
-                    bsum[6] += __uint_as_float(w3 << 16); bsum[7] += __uint_as_float(w3 & 0xffff0000u);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(&s_bias[c8 * 8 + e], bsum[e]);
+            }
+            ptx::named_bar_sync(1, kEpiThreads);
+            if (has_bias) {
+                for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
+            }
+        }
+        // ---- flush the TMEM-resident dW^T block: lane = input index (contiguous in dW rows -> coalesced REDs). All eight
+        //      warps take part (warp w reads TMEM lanes 32 (w % 4)..; the service warps take the odd (M block, column group)
+        //      pairs): 29 -> 15 us for a 256 x 256 block.
+        __syncwarp();
+        {
+            const uint32_t q = (uint32_t)(warp & 3);
+            const int half = warp >> 2;
+            ptx::mbar_wait(bars + 8 * (2 * kWgStages), (uint32_t)(seg & 1));
+            ptx::tc_fence_after();
+            if (seg == wk.n_seg - 1 && threadIdx.x == 128 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 2] = global_ns();
+            const int n_groups = N >> 5, n_pairs = mblocks * n_groups;
+            for (int pi = half; pi < n_pairs; pi += 2) {
+                const int mb = pi / n_groups, g = pi % n_groups;
+                const int m = mb * 128 + (int)(q * 32) + lane;
+                uint32_t r[32];
+                ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)g * 32u, r);
+                ptx::tmem_ld_wait();
+                if (m < u.m_valid) {
+#pragma unroll
+                    for (int jn = 0; jn < 32; ++jn) {
+                        const int n = g * 32 + jn;
+                        if (n < u.n_valid) atomicAdd(a.grads + u.w_base + (int64_t)n * u.w_row_stride + m, __uint_as_float(r[jn]));
+                    }
                 }
             }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(bars + 8 * (kWgStages + stage));
-            if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
         }
-        if (has_bias) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) atomicAdd(&s_bias[c8 * 8 + e], bsum[e]);
-        }
-        ptx::named_bar_sync(1, kEpiThreads);
-        if (has_bias) {
-            for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
-        }
-        // flush the TMEM-resident dW^T block: lane = input index (contiguous in dW rows -> coalesced REDs)
-        ptx::mbar_wait(bars + 8 * (2 * kWgStages), 0);
+        ptx::tc_fence_before();
+        __syncthreads();     // every warp has drained its accumulator columns before the next segment's first MMA overwrites them
         ptx::tc_fence_after();
-        if (tid == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 2] = global_ns();
-        // the CTAs of a unit finish together and add into the same dW block: each starts at a different (M block, column
-        // group) so they do not queue on the same L2 lines
-        const int n_groups = N >> 5, n_pairs = mblocks * n_groups;
-        for (int pi = 0; pi < n_pairs; ++pi) {
-            const int pr = (pi + (int)blockIdx.x) % n_pairs;
-            const int mb = pr / n_groups, g = pr % n_groups;
-            const int m = mb * 128 + (int)(q * 32) + lane;
-            uint32_t r[32];
-            ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)g * 32u, r);
-            ptx::tmem_ld_wait();
-            if (m < u.m_valid) {
-#pragma unroll
-                for (int jn = 0; jn < 32; ++jn) {
-                    const int n = g * 32 + jn;
-                    if (n < u.n_valid) atomicAdd(a.grads + u.w_base + (int64_t)n * u.w_row_stride + m, __uint_as_float(r[jn]));
-                }
-            }
-        }
     }
-    ptx::tc_fence_before();
-    __syncthreads();
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
     if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 3] = global_ns();
 }
@@ -871,53 +880,48 @@ static void build_work(TcState *s, int64_t n_tiles, cudaStream_t st) {
     if (s->work_tiles == n_tiles) return;
     const int G = s->num_sms;
     const int U = (int)s->plan.units.size();
-    std::vector<int> cost(U), cnt(U);
-    int total = 0;
-    // measured per half-tile iteration (tools/wgrad_marks.py): 0.42 us + 0.10 us per 8 KB half panel -- a ring stage costs a
-    // fixed latency on top of its bytes, so small units need more CTAs than their byte share
-    // (+ ~0.08 us when a one-M-block unit also sums biases: its epilogue pass outlasts its four MMAs). Costs in 0.01 us.
+    // Cost of one tile of a unit in ns, fitted to tools/wgrad_marks.py: a half-tile ring iteration takes 516 ns + 87 ns per
+    // 8 KB half panel -- a stage costs a fixed latency on top of its bytes -- (+ ~80 ns when a one-M-block unit also sums
+    // biases: its epilogue pass outlasts its four MMAs). A segment adds its ring fill + accumulator flush (~20 us).
+    std::vector<int64_t> tile_cost(U);
+    int64_t total = 0;
     for (int i = 0; i < U; ++i) {
         const WgradUnit &u = s->plan.units[i];
-        cost[i] = 10 * (u.n_p + u.n_q) + 40 + ((u.b_base >= 0 && u.n_p <= 2 && u.n_q >= 4) ? 8 : 0);
-        total += cost[i];
+        tile_cost[i] = 2 * (87 * (u.n_p + u.n_q) + 516 + ((u.b_base >= 0 && u.n_p <= 2 && u.n_q >= 4) ? 80 : 0));
+        total += tile_cost[i] * n_tiles;
     }
-    int used = 0;
-    for (int i = 0; i < U; ++i) {
-        int c = (int)((int64_t)G * cost[i] / total);
-        if (c < 1) c = 1;
-        if (c > n_tiles) c = (int)n_tiles;
-        cnt[i] = c;
-        used += c;
-    }
-    // hand out leftovers to the most loaded units (tiles per CTA), never exceeding n_tiles CTAs per unit
-    while (used < G) {
-        int best = -1;
-        double bl = 0;
-        for (int i = 0; i < U; ++i) {
-            if (cnt[i] >= n_tiles) continue;
-            const double load = (double)cost[i] / cnt[i];
-            if (load > bl) { bl = load; best = i; }
+    const int64_t seg_cost = 20000;
+    std::vector<WgradWork> work;
+    // the CTAs walk the units in order, each taking `budget` worth of cost; returns whether everything was placed
+    auto place = [&](int64_t budget) -> bool {
+        work.assign((size_t)G, WgradWork{});
+        int unit = 0;
+        int64_t tile = 0;   // next unassigned tile of `unit`
+        for (int c = 0; c < G && unit < U; ++c) {
+            int64_t left = budget;
+            WgradWork &w = work[c];
+            while (unit < U && w.n_seg < kWgMaxSeg) {
+                const int64_t fit = (left - seg_cost) / tile_cost[unit];
+                if (fit < (w.n_seg ? 8 : 1)) break;     // not worth opening another segment for a few tiles
+                const int64_t take = fit < n_tiles - tile ? fit : n_tiles - tile;
+                w.seg[w.n_seg].unit = unit;
+                w.seg[w.n_seg].tile_begin = (int)tile;
+                w.seg[w.n_seg].tile_end = (int)(tile + take);
+                ++w.n_seg;
+                left -= seg_cost + take * tile_cost[unit];
+                tile += take;
+                if (tile >= n_tiles) { ++unit; tile = 0; }
+            }
         }
-        if (best < 0) break;
-        ++cnt[best];
-        ++used;
+        return unit >= U;
+    };
+    int64_t lo = total / G, hi = total + seg_cost * (U + 1) + 1;   // hi: one CTA could take everything (kWgMaxSeg permitting)
+    while (!place(hi)) hi *= 2;
+    while (hi - lo > 64) {   // smallest budget that places everything
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (place(mid)) hi = mid; else lo = mid;
     }
-    while (used > G) {  // only possible when G < U
-        int best = -1;
-        for (int i = 0; i < U; ++i) if (cnt[i] > 1 && (best < 0 || cnt[i] > cnt[best])) best = i;
-        if (best < 0) break;
-        --cnt[best];
-        --used;
-    }
-    std::vector<WgradWork> work((size_t)G, WgradWork{0, 0, 0});
-    int c = 0;
-    for (int i = 0; i < U && c < G; ++i) {
-        for (int k = 0; k < cnt[i] && c < G; ++k, ++c) {
-            work[c].unit = i;
-            work[c].tile_begin = (int)(n_tiles * k / cnt[i]);
-            work[c].tile_end = (int)(n_tiles * (k + 1) / cnt[i]);
-        }
-    }
+    place(hi);
     cudaMemcpyAsync(s->d_work, work.data(), sizeof(WgradWork) * (size_t)G, cudaMemcpyHostToDevice, st);
     cudaStreamSynchronize(st);  // `work` is a host temporary
     s->work_tiles = n_tiles;
@@ -928,7 +932,7 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
     const int64_t n_tiles = (n + NERF_TILE_M - 1) / NERF_TILE_M;
     if (n_tiles == 0) return 0;
     if (n_tiles > s->max_tiles) { s->err = "tc_backward: batch exceeds the saved-activation capacity"; return -1; }
-    if ((int)s->plan.units.size() > s->num_sms) { s->err = "tc_backward: fewer SMs than weight-gradient units"; return -1; }
+    if ((int)s->plan.units.size() > kWgMaxSeg * s->num_sms) { s->err = "tc_backward: too few SMs for the weight-gradient units"; return -1; }
     build_work(s, n_tiles, st);
     ChainArgs a;
     memset(&a, 0, sizeof(a));
@@ -991,11 +995,17 @@ int tc_debug_wgrad_marks(TcState *s, unsigned long long *out, int capacity_ctas,
     if (cudaMemcpy(work.data(), s->d_work, sizeof(WgradWork) * G, cudaMemcpyDeviceToHost) != cudaSuccess) return -3;
     for (int i = 0; i < G; ++i) {
         for (int k = 0; k < 4; ++k) out[8 * i + k] = marks[4 * i + k];
-        out[8 * i + 4] = (unsigned long long)work[i].unit;
-        out[8 * i + 5] = (unsigned long long)work[i].tile_begin;
-        out[8 * i + 6] = (unsigned long long)work[i].tile_end;
-        const WgradUnit &u = s->plan.units[work[i].unit];
-        out[8 * i + 7] = (unsigned long long)(u.n_p + u.n_q);
+        int64_t iters = 0, bytes = 0;
+        for (int k = 0; k < work[i].n_seg; ++k) {
+            const WgradUnit &u = s->plan.units[work[i].seg[k].unit];
+            const int64_t it = 2 * (int64_t)(work[i].seg[k].tile_end - work[i].seg[k].tile_begin);
+            iters += it;
+            bytes += it * (u.n_p + u.n_q) * 8192;
+        }
+        out[8 * i + 4] = work[i].n_seg > 0 ? (unsigned long long)work[i].seg[0].unit : 0ull;
+        out[8 * i + 5] = (unsigned long long)work[i].n_seg;
+        out[8 * i + 6] = (unsigned long long)iters;
+        out[8 * i + 7] = (unsigned long long)bytes;
     }
     return G;
 }

@@ -90,8 +90,10 @@ struct WgradUnit {
     int32_t w_row_stride;   // in_dim of the layer (distance between consecutive out rows)
     int64_t b_base;         // float offset of db[out 0], or -1
 };
-struct WgradWork {          // one CTA's assignment
-    int32_t unit, tile_begin, tile_end;
+#define kWgMaxSeg 3
+struct WgradWork {          // one CTA's assignment: up to kWgMaxSeg (unit, tile range) segments, processed in order
+    int32_t n_seg;
+    struct { int32_t unit, tile_begin, tile_end; } seg[kWgMaxSeg];
 };
 
 struct PackChunk {

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-CTA timeline of k_wgrad at the bench shape: which unit / CTA finishes last, and how long the ring takes to fill."""
+"""Per-CTA timeline of k_wgrad at the bench shape: how evenly the CTAs finish, ring fill and accumulator-flush tails."""
 import ctypes
 import sys, os
 import numpy as np
@@ -8,9 +8,10 @@ sys.path.insert(0, ROOT)
 import nerf_rs_b200 as nb
 from oracle import model_torch as M
 
-cfg = nb.default_config()
+hidden = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+cfg = nb.default_config(hidden=hidden)
 m = nb.NeRF(cfg)
-m.set_weights(M.flatten_params(M.init_params(M.ModelConfig(hidden=256), 0)).numpy())
+m.set_weights(M.flatten_params(M.init_params(M.ModelConfig(hidden=hidden), 0)).numpy())
 rng = np.random.default_rng(1)
 ang = nb.get_view_angles(6)
 m.set_images(rng.random((len(ang), 800 * 800, 4), dtype=np.float32))
@@ -22,15 +23,16 @@ out = np.zeros((256, 8), dtype=np.uint64)
 n = m.lib.nerf_debug_wgrad_marks(m.h, out.ctypes.data_as(ctypes.c_void_p), 256)
 assert n > 0, n
 o = out[:n].astype(np.int64)
+print('idle CTAs', int((o[:, 5] == 0).sum()))
+o = o[o[:, 5] > 0]
 t0 = o[:, 0].min()
-dur = (o[:, 3] - o[:, 0]) / 1e3
-print("kernel span us", (o[:, 3].max() - t0) / 1e3, "start skew us", (o[:, 0].max() - t0) / 1e3)
-print("unit panels ctas tiles/cta  first_stage_us  mma_done_us(min/max)  end_us(min/max)")
-for u in sorted(set(o[:, 4])):
-    r = o[o[:, 4] == u]
-    tiles = r[:, 6] - r[:, 5]
-    print(int(u), int(r[0, 7]), len(r), tiles.min(), tiles.max(), round(float(((r[:, 1] - r[:, 0]) / 1e3).mean()), 1),
-          round(float((r[:, 2] - t0).min() / 1e3), 1), round(float((r[:, 2] - t0).max() / 1e3), 1),
-          round(float((r[:, 3] - t0).min() / 1e3), 1), round(float((r[:, 3] - t0).max() / 1e3), 1))
-us_per_iter = (o[:, 2] - o[:, 1]) / 1e3 / np.maximum(1, 2 * (o[:, 6] - o[:, 5]))
-print("us per half tile by panels:", {int(p): round(float(us_per_iter[o[:, 7] == p].mean()), 3) for p in sorted(set(o[:, 7]))})
+end = (o[:, 3] - t0) / 1e3
+mma = (o[:, 2] - t0) / 1e3
+print("kernel span us", round(float(end.max()), 1), "start skew us", (o[:, 0].max() - t0) / 1e3)
+print("CTA end us: min %.1f  p10 %.1f  median %.1f  p90 %.1f  max %.1f" % (end.min(), np.percentile(end, 10), np.median(end), np.percentile(end, 90), end.max()))
+print("last MMA done us: min %.1f median %.1f max %.1f ; flush tail us mean %.1f" % (mma.min(), np.median(mma), mma.max(), float((end - mma).mean())))
+print("ring fill us mean %.1f" % float(((o[:, 1] - o[:, 0]) / 1e3).mean()))
+print("segments per CTA:", {int(k): int((o[:, 5] == k).sum()) for k in sorted(set(o[:, 5]))})
+print("GB loaded %.3f -> %.0f GB/s over the span" % (o[:, 7].sum() / 1e9, o[:, 7].sum() / 1e9 / (end.max() * 1e-6)))
+late = np.argsort(end)[-5:]
+print("slowest CTAs (cta, first unit, segs, iters, end us):", [(int(i), int(o[i, 4]), int(o[i, 5]), int(o[i, 6]), round(float(end[i]), 1)) for i in late])
