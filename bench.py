@@ -56,7 +56,8 @@ def ncu_traffic():
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_summary.json"))):
         for k in json.load(open(f)).get("kernels", []):
             nm = {"k_chain<0, 1>": "mlp_fwd_train", "k_chain<1, 1>": "mlp_dgrad", "k_wgrad": "mlp_wgrad", "k_chain<0, 0>": "mlp_fwd",
-                  "k_chain2<0, 1>": "mlp_fwd_train", "k_chain2<1, 1>": "mlp_dgrad", "k_chain2<0, 0>": "mlp_fwd"}.get(k["kernel"])
+                  "k_chain2<0, 1>": "mlp_fwd_train", "k_chain2<1, 1>": "mlp_dgrad", "k_chain2<0, 0>": "mlp_fwd",
+                  "k_chain2<0, 1, 0>": "mlp_fwd_train", "k_chain2<1, 1, 0>": "mlp_dgrad", "k_chain2<0, 0, 0>": "mlp_fwd"}.get(k["kernel"])
             if nm and "dram_traffic_bytes" in k:
                 out[nm] = {"bytes": k["dram_traffic_bytes"], "source": os.path.basename(f)}
     return out
