@@ -61,6 +61,8 @@ pub mod sys {
         pub fn nerf_get_adam_state(ctx: *mut nerf_ctx, m: *mut f32, v: *mut f32, n: i64, step: *mut i64) -> c_int;
         pub fn nerf_set_adam_state(ctx: *mut nerf_ctx, m: *const f32, v: *const f32, n: i64, step: i64) -> c_int;
         pub fn nerf_set_images(ctx: *mut nerf_ctx, rgba: *const f32, n_views: i32) -> c_int;
+        pub fn nerf_set_images_rgba8(ctx: *mut nerf_ctx, rgba8: *const u8, n_views: i32) -> c_int;
+        pub fn nerf_load_png_rgba8(path: *const c_char, out: *mut u8, capacity_bytes: i64, width: *mut i32, height: *mut i32) -> c_int;
         pub fn nerf_set_view_angles(ctx: *mut nerf_ctx, yaw_pitch: *const f32, n_angles: i32) -> c_int;
         pub fn nerf_view_angles_grid(n: i32, out: *mut f32, capacity: i32) -> c_int;
         pub fn nerf_get_batch(ctx: *mut nerf_ctx, indices_yx: *const i64, view_index: *const i64, n_picks: i32,
@@ -120,6 +122,23 @@ pub struct NeRF {
     n_views: usize,
 }
 
+/// The decode step of `image_loading::load_image_as_array` (image_loading.rs:7): 8-bit RGBA PNG -> (bytes, width, height).
+/// Anything that is not RGBA8 is an error (the reference yields an empty Vec for it).
+pub fn load_image_rgba8(path: &str) -> Result<(Vec<u8>, usize, usize), NerfError> {
+    let c = std::ffi::CString::new(path).map_err(|_| NerfError { status: -1, message: "path contains NUL".into() })?;
+    let (mut w, mut h) = (0i32, 0i32);
+    check(std::ptr::null(), unsafe { sys::nerf_load_png_rgba8(c.as_ptr(), std::ptr::null_mut(), 0, &mut w, &mut h) })?;
+    let mut out = vec![0u8; (w as usize) * (h as usize) * 4];
+    check(std::ptr::null(), unsafe { sys::nerf_load_png_rgba8(c.as_ptr(), out.as_mut_ptr(), out.len() as i64, &mut w, &mut h) })?;
+    Ok((out, w as usize, h as usize))
+}
+
+/// `image_loading::load_image_as_array` (image_loading.rs:6-24): `[r, g, b, a]` per pixel, each `as f32 / 255.`.
+pub fn load_image_as_array(path: &str) -> Result<Vec<[f32; 4]>, NerfError> {
+    let (bytes, _, _) = load_image_rgba8(path)?;
+    Ok(bytes.chunks_exact(4).map(|p| [p[0] as f32 / 255., p[1] as f32 / 255., p[2] as f32 / 255., p[3] as f32 / 255.]).collect())
+}
+
 impl NeRF {
     /// `NeRF::new()` (model.rs:140) with the north-star defaults.
     pub fn new() -> Result<NeRF, NerfError> {
@@ -138,6 +157,14 @@ impl NeRF {
         let flat: Vec<f32> = imgs.iter().flatten().flatten().copied().collect();
         self.n_views = imgs.len();
         check(self.ctx, unsafe { sys::nerf_set_images(self.ctx, flat.as_ptr(), imgs.len() as i32) })
+    }
+
+    /// Residency from the decoded RGBA8 bytes of `load_image_rgba8` (4 B/pixel on the device; the sampler's gold gather
+    /// performs the `as f32 / 255.` of image_loading.rs:13-18, bit for bit).
+    pub fn set_images_rgba8(&mut self, imgs: &Vec<Vec<u8>>) -> Result<(), NerfError> {
+        let flat: Vec<u8> = imgs.iter().flatten().copied().collect();
+        self.n_views = imgs.len();
+        check(self.ctx, unsafe { sys::nerf_set_images_rgba8(self.ctx, flat.as_ptr(), imgs.len() as i32) })
     }
 
     pub fn set_view_angles(&mut self, view_angles: &Vec<(f32, f32)>) -> Result<(), NerfError> {

@@ -40,6 +40,25 @@ inline std::vector<std::pair<float, float>> get_view_angles(int num_views) {  //
     return out;
 }
 
+// image_loading::load_image_as_array's decode step (image_loading.rs:7): 8-bit RGBA PNG -> bytes; throws for anything else
+inline std::vector<uint8_t> load_image_rgba8(const std::string &path, int *width = nullptr, int *height = nullptr) {
+    int32_t w = 0, h = 0;
+    check(nullptr, nerf_load_png_rgba8(path.c_str(), nullptr, 0, &w, &h));
+    std::vector<uint8_t> out((size_t)w * h * 4);
+    check(nullptr, nerf_load_png_rgba8(path.c_str(), out.data(), (int64_t)out.size(), &w, &h));
+    if (width) *width = w;
+    if (height) *height = h;
+    return out;
+}
+// image_loading.rs:6-24: one [r,g,b,a] per pixel, each `as f32 / 255.`
+inline std::vector<std::array<float, 4>> load_image_as_array(const std::string &path) {
+    const std::vector<uint8_t> b = load_image_rgba8(path);
+    std::vector<std::array<float, 4>> out(b.size() / 4);
+    for (size_t i = 0; i < out.size(); ++i)
+        out[i] = {(float)b[4 * i] / 255.f, (float)b[4 * i + 1] / 255.f, (float)b[4 * i + 2] / 255.f, (float)b[4 * i + 3] / 255.f};
+    return out;
+}
+
 class NeRF {
    public:
     explicit NeRF(const nerf_config &cfg, int device = 0) : cfg_(cfg) { check(nullptr, nerf_create(&cfg_, device, &ctx_)); }
@@ -85,6 +104,13 @@ class NeRF {
         for (auto &im : imgs)
             for (auto &px : im) flat.insert(flat.end(), px.begin(), px.end());
         check(ctx_, nerf_set_images(ctx_, flat.data(), (int32_t)imgs.size()));
+        n_views_ = (int)imgs.size();
+    }
+    // residency from RGBA8 bytes (4 B/pixel on the device; the gold gather does the `as f32 / 255.` of image_loading.rs:13-18)
+    void set_images_rgba8(const std::vector<std::vector<uint8_t>> &imgs) {
+        std::vector<uint8_t> flat;
+        for (auto &im : imgs) flat.insert(flat.end(), im.begin(), im.end());
+        check(ctx_, nerf_set_images_rgba8(ctx_, flat.data(), (int32_t)imgs.size()));
         n_views_ = (int)imgs.size();
     }
     void set_view_angles(const std::vector<std::pair<float, float>> &va) {

@@ -11,6 +11,7 @@ SRC = r'''
 int main() {
     auto angles = nerf::get_view_angles(6);
     if (angles.size() != 84) return 2;
+    try { nerf::load_image_as_array("/nonexistent/image-0.png"); return 4; } catch (const nerf::Error &) {}   // image_loading.rs:6
     try {
         nerf::NeRF model;                      // NeRF::new(): needs a B200
         std::mt19937_64 rng(0);
