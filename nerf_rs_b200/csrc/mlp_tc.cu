@@ -462,7 +462,7 @@ constexpr int kWgStages = 3;
 constexpr uint32_t kWgStageBytes = 65536;
 constexpr uint32_t kWgHalf = 8192;  // 64 sample rows of one panel
 constexpr uint32_t kWgBars = kWgStages * kWgStageBytes;
-constexpr uint32_t kWgSmem = kWgBars + 8 * 8 + 16 + 256 * 4;
+constexpr uint32_t kWgSmem = kWgBars + 8 * 8 + 16 + 256 * 4 + 260 * 4 + kWgStages * 64 * 4;
 
 struct WgradArgs {
     const WgradUnit *units;
@@ -487,6 +487,8 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     const uint32_t bars = sbase + kWgBars;  // full[3], empty[3], done
     volatile uint32_t *tmem_ptr_smem = reinterpret_cast<volatile uint32_t *>(smem + kWgBars + 64);
     float *s_bias = reinterpret_cast<float *>(smem + kWgBars + 80);
+    float *s_sg = s_bias + 256;     // sigma-row slice (256) + its bias (1)
+    float *s_dsg = s_sg + 260;      // [stage][64] d(sigma) of the stage's sample rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const WgradWork wk = a.work[blockIdx.x];
     if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x] = global_ns();
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     if (threadIdx.x == 0) {
         if (sbase & 1023u) __trap();
         for (int s = 0; s < kWgStages; ++s) {
-            ptx::mbar_init(bars + 8 * s, 1);
+            ptx::mbar_init(bars + 8 * s, 2);                // producer (expect_tx) + the d(sigma) loader warp
             ptx::mbar_init(bars + 8 * (kWgStages + s), 5);  // MMA commit + 4 epilogue warps
         }
         ptx::mbar_init(bars + 8 * (2 * kWgStages), 1);
@@ -517,8 +519,9 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
         const int n_p = u.n_p, n_q = u.n_q;
         const int N = 64 * n_q;
         const int mblocks = (n_p + 1) >> 1;
+        const uint32_t mb_cols = mblocks > 2 ? (uint32_t)N : 256u;   // TMEM columns between M blocks (3 x 128 for the merged fc9 unit)
         const int n_iters = (tile_end - wk.seg[seg].tile_begin) * 2;
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_bias[i] = 0.f;
+        for (int i = threadIdx.x; i < 256 + 260; i += blockDim.x) s_bias[i] = 0.f;
         __syncthreads();
 
         if (warp == 0) {
@@ -552,13 +555,42 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
                             // 16 sample rows per K step = 2048 B; 64-element M/N blocks are kWgHalf apart
                             const uint64_t ad = ptx::umma_desc_sw128(st_addr + (uint32_t)(2 * mb) * kWgHalf + k * 2048u, kWgHalf, 1024);
                             const uint64_t bd = ptx::umma_desc_sw128(st_addr + (uint32_t)n_p * kWgHalf + k * 2048u, kWgHalf, 1024);
-                            ptx::umma_ss(tmem_base + (uint32_t)mb * 256u, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                            ptx::umma_ss(tmem_base + (uint32_t)mb * mb_cols, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
                         }
                     }
                     ptx::umma_commit(bars + 8 * (kWgStages + stage));
                     if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
                 }
                 ptx::umma_commit(bars + 8 * (2 * kWgStages));
+            }
+        } else if (warp == 3) {
+            // second arrival of every full barrier. For an fc8 feature unit it first stages column 0 of the d(sigma) panel for
+            // the stage's 64 sample rows (fp32 strip): the scattered global loads run as far ahead as the ring allows and
+            // never sit on the consumers' path. Ping-pong registers: half tile it+1 is in flight while it is handed over.
+            const bool sg = u.sg_slot >= 0;
+            const int r0 = lane, r1 = lane + 32;
+            auto fetch = [&](int it, uint16_t &v0, uint16_t &v1) {
+                const int tile = tile_end - 1 - (it >> 1);
+                const uint8_t *gb = a.grad_base + ((size_t)tile * a.grad_slots + (size_t)u.sg_slot) * kSlotBytes + (size_t)(it & 1) * kWgHalf;
+                v0 = __ldg(reinterpret_cast<const uint16_t *>(gb + r0 * 128 + ((r0 & 7) << 4)));
+                v1 = __ldg(reinterpret_cast<const uint16_t *>(gb + r1 * 128 + ((r1 & 7) << 4)));
+            };
+            auto step = [&](int it, uint16_t c0, uint16_t c1, uint16_t &n0, uint16_t &n1) {
+                if (sg && it + 1 < n_iters) fetch(it + 1, n0, n1);
+                ptx::mbar_wait(bars + 8 * (kWgStages + stage), phase ^ 1u);
+                if (sg) {
+                    s_dsg[stage * 64 + r0] = __uint_as_float((uint32_t)c0 << 16);
+                    s_dsg[stage * 64 + r1] = __uint_as_float((uint32_t)c1 << 16);
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bars + 8 * stage);
+                if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
+            };
+            uint16_t a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+            if (sg) fetch(0, a0, a1);
+            for (int it = 0; it < n_iters; it += 2) {   // two half tiles per tile: n_iters is even
+                step(it, a0, a1, b0, b1);
+                step(it + 1, b0, b1, a0, a1);
             }
         } else if (warp >= 4) {
             const int tid = threadIdx.x - 128;
@@ -569,9 +601,39 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
             const int n_rg = kEpiThreads / ccols;
             const int rpr = 64 / n_rg;           // rows per row group per half tile
             float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            // sigma row of fc8 on the CUDA cores (units with sg_slot >= 0, n_p <= 4): thread = 8 input features x a group of rows
+            const bool has_sg = u.sg_slot >= 0 && n_p <= 4;
+            const int pcols = n_p * 8;            // 16-byte chunk columns of P
+            const int pc8 = tid % pcols;
+            const int prg = tid / pcols;
+            const int n_prg = kEpiThreads / pcols;
+            const int rpp = (64 + n_prg - 1) / n_prg;   // sample rows per row group per half tile
+            const bool sg_active = has_sg && prg < n_prg;
+            float ssum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float dsum = 0.f;
             for (int it = 0; it < n_iters; ++it) {
                 ptx::mbar_wait(bars + 8 * stage, phase);
                 if (seg == 0 && it == 0 && tid == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 1] = global_ns();
+                if (sg_active) {
+                    const uint32_t paddr = sbase + stage * kWgStageBytes + (uint32_t)(pc8 >> 3) * kWgHalf;
+                    const float *dsg = s_dsg + stage * 64;
+#pragma unroll 4
+                    for (int rr = 0; rr < rpp; ++rr) {
+                        const uint32_t r = (uint32_t)(prg * rpp + rr);
+                        if (r < 64u) {
+                            const float d = dsg[r];
+                            uint32_t w0, w1, w2, w3;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                         : "r"(panel_chunk_addr(paddr, r, (uint32_t)(pc8 & 7))));
+                            ssum[0] += d * __uint_as_float(w0 << 16); ssum[1] += d * __uint_as_float(w0 & 0xffff0000u);
+                            ssum[2] += d * __uint_as_float(w1 << 16); ssum[3] += d * __uint_as_float(w1 & 0xffff0000u);
+                            ssum[4] += d * __uint_as_float(w2 << 16); ssum[5] += d * __uint_as_float(w2 & 0xffff0000u);
+                            ssum[6] += d * __uint_as_float(w3 << 16); ssum[7] += d * __uint_as_float(w3 & 0xffff0000u);
+                            if (pc8 == 0) dsum += d;
+                        }
+                    }
+                }
                 if (has_bias) {
                     const uint32_t qaddr = sbase + stage * kWgStageBytes + (uint32_t)(n_p + (c8 >> 3)) * kWgHalf;
                     for (int rr = 0; rr < rpr; ++rr) {
@@ -594,9 +656,18 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) atomicAdd(&s_bias[c8 * 8 + e], bsum[e]);
             }
+            if (sg_active) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(&s_sg[pc8 * 8 + e], ssum[e]);
+                if (pc8 == 0) atomicAdd(&s_sg[256], dsum);
+            }
             ptx::named_bar_sync(1, kEpiThreads);
             if (has_bias) {
                 for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
+            }
+            if (has_sg) {
+                for (int m = tid; m < u.m_valid; m += kEpiThreads) atomicAdd(a.grads + u.sg_w_base + m, s_sg[m]);
+                if (tid == 0 && u.sg_b_base >= 0) atomicAdd(a.grads + u.sg_b_base, s_sg[256]);
             }
         }
         // ---- flush the TMEM-resident dW^T block: lane = input index (contiguous in dW rows -> coalesced REDs). All eight
@@ -614,7 +685,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
                 const int mb = pi / n_groups, g = pi % n_groups;
                 const int m = mb * 128 + (int)(q * 32) + lane;
                 uint32_t r[32];
-                ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * 256u + (uint32_t)g * 32u, r);
+                ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * mb_cols + (uint32_t)g * 32u, r);
                 ptx::tmem_ld_wait();
                 if (m < u.m_valid) {
 #pragma unroll
@@ -887,7 +958,7 @@ static void build_work(TcState *s, int64_t n_tiles, cudaStream_t st) {
     int64_t total = 0;
     for (int i = 0; i < U; ++i) {
         const WgradUnit &u = s->plan.units[i];
-        tile_cost[i] = 2 * (87 * (u.n_p + u.n_q) + 516 + ((u.b_base >= 0 && u.n_p <= 2 && u.n_q >= 4) ? 80 : 0));
+        tile_cost[i] = 2 * (87 * (u.n_p + u.n_q) + 516 + ((u.b_base >= 0 && u.n_p <= 2 && u.n_q >= 4) ? 80 : 0) + (u.sg_slot >= 0 ? 630 : 0));
         total += tile_cost[i] * n_tiles;
     }
     const int64_t seg_cost = 20000;

@@ -81,14 +81,18 @@ struct EpiJob {
 
 // weight gradient unit: dW^T[in x out] block = P^T (inputs, M side) x Q (pre-activation grads, N side)
 struct WgradUnit {
-    uint8_t n_p, n_q;       // panels on the M side (1..4) and N side (1..4)
+    uint8_t n_p, n_q;       // panels on the M side (1..5; 5 only with n_q <= 2) and N side (1..4)
     uint8_t pad[2];
-    int16_t p_slot[4];      // per-tile slots in the activation area
+    int16_t p_slot[6];      // per-tile slots in the activation area
     int16_t q_slot[4];      // per-tile slots in the gradient area
+    int16_t sg_slot;        // >= 0: gradient-area slot of the d(sigma) panel -- the unit also produces the sigma row of fc8,
+    int16_t pad1;           //       dW[sigma][m] = sum_s dsigma[s] P[s][m], on the CUDA cores from the P panels it already holds
     int32_t m_valid, n_valid;  // unpadded extents
     int64_t w_base;         // float offset of dW[out 0][in 0] of this block in the flat gradient blob
     int32_t w_row_stride;   // in_dim of the layer (distance between consecutive out rows)
     int64_t b_base;         // float offset of db[out 0], or -1
+    int64_t sg_w_base;      // float offset of dW[sigma row][in 0 of this block]
+    int64_t sg_b_base;      // float offset of db[sigma], or -1
 };
 #define kWgMaxSeg 3
 struct WgradWork {          // one CTA's assignment: up to kWgMaxSeg (unit, tile range) segments, processed in order

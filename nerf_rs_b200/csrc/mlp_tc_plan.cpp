@@ -356,7 +356,11 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
         memset(&u, 0, sizeof(u));
         u.n_p = (uint8_t)n_p;
         u.n_q = (uint8_t)n_q;
-        for (int i = 0; i < 4; ++i) { u.p_slot[i] = (int16_t)(i < n_p ? p0 + i : -1); u.q_slot[i] = (int16_t)(i < n_q ? q0 + i : -1); }
+        for (int i = 0; i < 6; ++i) u.p_slot[i] = (int16_t)(i < n_p ? p0 + i : -1);
+        for (int i = 0; i < 4; ++i) u.q_slot[i] = (int16_t)(i < n_q ? q0 + i : -1);
+        u.sg_slot = -1;
+        u.sg_w_base = 0;
+        u.sg_b_base = -1;
         u.m_valid = m_valid;
         u.n_valid = n_valid;
         u.w_base = w_base;
@@ -391,13 +395,34 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     }
     {
         const LayerGeom &L = g.L[7];
-        add_block(np, sl.H(7), 1, sl.Sg(), g.W, 1, L.w_off, L.in_dim, L.b_off);  // sigma row
-        if (g.use_rgb_head) add_block(np, sl.H(7), np, sl.dFeat(), g.W, g.W, L.w_off + L.in_dim, L.in_dim, L.b_off + 1);
+        if (!g.use_rgb_head) {
+            add_block(np, sl.H(7), 1, sl.Sg(), g.W, 1, L.w_off, L.in_dim, L.b_off);  // sigma row
+        } else {
+            // fc8 = [sigma row ; feature rows]. The feature units hold the H7 panels anyway: the ones of the first Q block also
+            // produce their slice of the sigma row on the CUDA cores (a 1-column GEMM would re-read all of H7 for 1/256 of the work)
+            const size_t first = plan.units.size();
+            add_block(np, sl.H(7), np, sl.dFeat(), g.W, g.W, L.w_off + L.in_dim, L.in_dim, L.b_off + 1);
+            for (size_t i = first; i < plan.units.size(); ++i) {
+                WgradUnit &u = plan.units[i];
+                if (u.q_slot[0] != sl.dFeat()) continue;          // only the units of the first Q block
+                const int pa = u.p_slot[0] - sl.H(7);             // first H7 panel of this unit
+                u.sg_slot = (int16_t)sl.Sg();
+                u.sg_w_base = L.w_off + 64 * pa;
+                u.sg_b_base = pa == 0 ? L.b_off : -1;
+            }
+        }
     }
     if (g.use_rgb_head) {
         const LayerGeom &L9 = g.L[8], &L10 = g.L[9];
-        add_block(np, sl.feat(), np2, sl.dP9(), g.W, g.W2, L9.w_off, L9.in_dim, L9.b_off);
-        if (g.Cd) add_block(1, sl.D(), np2, sl.dP9(), g.Cd, g.W2, L9.w_off + g.W, L9.in_dim, -1);
+        if (g.Cd && np <= 4 && np2 <= 2 && g.W % 64 == 0) {
+            // fc9 over [features ; encoded direction] as ONE unit (5 M-side panels x <= 128 columns fit TMEM as 3 x 128):
+            // dP9 is read once instead of once per input block
+            add_unit(np + 1, sl.feat(), np2, sl.dP9(), g.W + g.Cd, g.W2, L9.w_off, L9.in_dim, L9.b_off);
+            plan.units.back().p_slot[np] = (int16_t)sl.D();
+        } else {
+            add_block(np, sl.feat(), np2, sl.dP9(), g.W, g.W2, L9.w_off, L9.in_dim, L9.b_off);
+            if (g.Cd) add_block(1, sl.D(), np2, sl.dP9(), g.Cd, g.W2, L9.w_off + g.W, L9.in_dim, -1);
+        }
         add_block(np2, sl.h9(), 1, sl.R(), g.W2, 4, L10.w_off, L10.in_dim, L10.b_off);
     }
     plan.e_slot = np > 4 ? TC_SLOT_E_WIDE : TC_SLOT_E;

@@ -20,9 +20,9 @@ EPI_JOB = np.dtype([("kind", "u1"), ("acc", "u1"), ("ncols", "u1"), ("out_slot",
                     ("mask_word0", "<u2"), ("bias_off", "<u2"), ("acc_col", "<u2")])
 PACK_CHUNK = np.dtype([("dst_off", "<u4"), ("n_rows", "<i4"), ("src_base", "<i8"), ("row_stride", "<i4"),
                        ("col_stride", "<i4"), ("valid_rows", "<i4"), ("valid_cols", "<i4")])
-WGRAD_UNIT = np.dtype([("n_p", "u1"), ("n_q", "u1"), ("pad", "u1", (2,)), ("p_slot", "<i2", (4,)), ("q_slot", "<i2", (4,)),
-                       ("m_valid", "<i4"), ("n_valid", "<i4"), ("pad2", "<i4"), ("w_base", "<i8"), ("w_row_stride", "<i4"),
-                       ("pad3", "<i4"), ("b_base", "<i8")])
+WGRAD_UNIT = np.dtype([("n_p", "u1"), ("n_q", "u1"), ("pad", "u1", (2,)), ("p_slot", "<i2", (6,)), ("q_slot", "<i2", (4,)),
+                       ("sg_slot", "<i2"), ("pad1", "<i2"), ("m_valid", "<i4"), ("n_valid", "<i4"), ("pad2", "<i4"), ("w_base", "<i8"),
+                       ("w_row_stride", "<i4"), ("pad3", "<i4"), ("b_base", "<i8"), ("sg_w_base", "<i8"), ("sg_b_base", "<i8")])
 PACK_BIAS = np.dtype([("dst_off", "<u4"), ("pad", "<u4"), ("src_base", "<i8"), ("count", "<i4"), ("padded", "<i4")])
 
 NONE = 0xFF
@@ -174,6 +174,12 @@ def emulate_wgrad(plan, act, grad, n_params):
             g[base:base + mv] += dwt[:mv, n]
         if u["b_base"] >= 0:
             g[int(u["b_base"]):int(u["b_base"]) + nv] += Q[:, :nv].sum(0)
+        if u["sg_slot"] >= 0:   # sigma row of fc8 from the same P panels (CUDA cores in k_wgrad)
+            ds = grad[int(u["sg_slot"])][:, 0].astype(np.float64)
+            g[int(u["sg_w_base"]):int(u["sg_w_base"]) + mv] += P[:, :mv].T @ ds
+            if u["sg_b_base"] >= 0:
+                g[int(u["sg_b_base"])] += ds.sum()
+        assert int(u["n_p"]) <= 4 or (int(u["n_q"]) <= 2 and u["sg_slot"] < 0), "5 M-side panels need N <= 128 (TMEM 3 x 128 columns)"
     return g.astype(np.float32)
 
 
