@@ -46,6 +46,16 @@ pub mod sys {
         _private: [u8; 0],
     }
 
+    /// Host output pointers of `nerf_log_metrics` (null = skip); see include/nerf_b200.h.
+    #[repr(C)]
+    pub struct nerf_metrics {
+        pub screen_x: *mut f64, pub screen_y: *mut f64, pub t_hist: *mut f64,
+        pub world_yx: *mut u32, pub world_zx: *mut u32, pub world_yz: *mut u32,
+        pub density_x: *mut f64, pub density_y: *mut f64, pub density_z: *mut f64,
+        pub density_yx: *mut u32, pub density_zx: *mut u32, pub density_yz: *mut u32,
+        pub prediction: *mut u32,
+    }
+
     extern "C" {
         pub fn nerf_abi_version() -> c_int;
         pub fn nerf_default_config(cfg: *mut nerf_config) -> c_int;
@@ -61,6 +71,7 @@ pub mod sys {
         pub fn nerf_get_adam_state(ctx: *mut nerf_ctx, m: *mut f32, v: *mut f32, n: i64, step: *mut i64) -> c_int;
         pub fn nerf_set_adam_state(ctx: *mut nerf_ctx, m: *const f32, v: *const f32, n: i64, step: i64) -> c_int;
         pub fn nerf_set_images(ctx: *mut nerf_ctx, rgba: *const f32, n_views: i32) -> c_int;
+        pub fn nerf_log_metrics(ctx: *mut nerf_ctx, out: *const nerf_metrics) -> c_int;
         pub fn nerf_set_images_rgba8(ctx: *mut nerf_ctx, rgba8: *const u8, n_views: i32) -> c_int;
         pub fn nerf_load_png_rgba8(path: *const c_char, out: *mut u8, capacity_bytes: i64, width: *mut i32, height: *mut i32) -> c_int;
         pub fn nerf_set_view_angles(ctx: *mut nerf_ctx, yaw_pitch: *const f32, n_angles: i32) -> c_int;
@@ -165,6 +176,37 @@ impl NeRF {
         let flat: Vec<u8> = imgs.iter().flatten().copied().collect();
         self.n_views = imgs.len();
         check(self.ctx, unsafe { sys::nerf_set_images_rgba8(self.ctx, flat.as_ptr(), imgs.len() as i32) })
+    }
+
+    /// `log_screen_coords` + `log_query_distances` (logging.rs:13-39) for the resident batch, computed on the device:
+    /// (screen_x [W], screen_y [H], t [2000]) bucket counts, ready for `log_as_hist` (logging.rs:266-283).
+    pub fn log_batch_histograms(&self) -> Result<(Vec<f64>, Vec<f64>, Vec<f64>), NerfError> {
+        let (mut sx, mut sy, mut t) = (vec![0f64; self.cfg.image_w as usize], vec![0f64; self.cfg.image_h as usize], vec![0f64; 2000]);
+        let mut m: sys::nerf_metrics = unsafe { std::mem::zeroed() };
+        m.screen_x = sx.as_mut_ptr();
+        m.screen_y = sy.as_mut_ptr();
+        m.t_hist = t.as_mut_ptr();
+        check(self.ctx, unsafe { sys::nerf_log_metrics(self.ctx, &m) })?;
+        Ok((sx, sy, t))
+    }
+
+    /// `log_query_points_as_maps` (logging.rs:41-107): the yx / zx / yz occupancy maps, 100x100 0x00RRGGBB each.
+    pub fn log_query_point_maps(&self) -> Result<[Vec<u32>; 3], NerfError> {
+        let mut maps = [vec![0u32; 10000], vec![0u32; 10000], vec![0u32; 10000]];
+        let mut m: sys::nerf_metrics = unsafe { std::mem::zeroed() };
+        m.world_yx = maps[0].as_mut_ptr();
+        m.world_zx = maps[1].as_mut_ptr();
+        m.world_yz = maps[2].as_mut_ptr();
+        check(self.ctx, unsafe { sys::nerf_log_metrics(self.ctx, &m) })?;
+        Ok(maps)
+    }
+
+    /// `draw_predictions` (display.rs:96-110): the batch's predicted pixels scattered into a WIDTH x HEIGHT back buffer.
+    pub fn draw_predictions(&self, backbuffer: &mut [u32]) -> Result<(), NerfError> {
+        assert_eq!(backbuffer.len(), (self.cfg.image_w * self.cfg.image_h) as usize);
+        let mut m: sys::nerf_metrics = unsafe { std::mem::zeroed() };
+        m.prediction = backbuffer.as_mut_ptr();
+        check(self.ctx, unsafe { sys::nerf_log_metrics(self.ctx, &m) })
     }
 
     pub fn set_view_angles(&mut self, view_angles: &Vec<(f32, f32)>) -> Result<(), NerfError> {

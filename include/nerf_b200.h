@@ -189,6 +189,26 @@ int nerf_profile_read(nerf_ctx *ctx, char *names /*[capacity][32]*/, float *tota
 int64_t nerf_launch_count(const nerf_ctx *ctx);  /* kernels launched by this context so far */
 int nerf_flush_l2(nerf_ctx *ctx);                /* overwrite a >L2-sized scratch buffer */
 
+/* ---- per-batch logging projections (src/logging.rs, src/display.rs:96-110) computed on the device from the resident batch.
+ * Every pointer is a caller-owned HOST buffer or NULL to skip that output. Density outputs and `prediction` need a
+ * preceding nerf_predict* on the batch (NERF_ERR_STATE otherwise). */
+typedef struct nerf_metrics {
+    double *screen_x;        /* [image_w]  log_screen_coords (logging.rs:13-25): counts of indices[r][0] -- the reference binds `[x, y]` to the stored [y, x] pair */
+    double *screen_y;        /* [image_h]  counts of indices[r][1] */
+    double *t_hist;          /* [2000]     log_query_distances (logging.rs:27-39): bucket floor(500 t) */
+    uint32_t *world_yx;      /* [100*100]  log_query_points_as_maps (logging.rs:41-107): 0x00FFFFFF where a sample lands */
+    uint32_t *world_zx;
+    uint32_t *world_yz;
+    double *density_x;       /* [2000]     log_densities (logging.rs:109-134): density sums per bucket floor(500 (w + 1)) */
+    double *density_y;
+    double *density_z;
+    uint32_t *density_yx;    /* [100*100]  log_density_maps (logging.rs:136-195): last sample's max(density, 0) as 0x00RRGGBB */
+    uint32_t *density_zx;
+    uint32_t *density_yz;
+    uint32_t *prediction;    /* [image_h*image_w] draw_predictions (display.rs:96-110): the batch's pixels as 0x00RRGGBB, 0 elsewhere */
+} nerf_metrics;
+int nerf_log_metrics(nerf_ctx *ctx, const nerf_metrics *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,12 @@ i32, i64, u64, f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_f
 P = ctypes.POINTER
 
 # name -> (restype, argtypes); exactly the declarations of include/nerf_b200.h + nerf_b200_debug.h
+class NerfMetrics(ctypes.Structure):
+    """nerf_metrics (include/nerf_b200.h): host output pointers of nerf_log_metrics, NULL = skip."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("screen_x", "screen_y", "t_hist", "world_yx", "world_zx", "world_yz", "density_x",
+                                                 "density_y", "density_z", "density_yx", "density_zx", "density_yz", "prediction")]
+
+
 SIGNATURES = {
     "nerf_abi_version": (ctypes.c_int, []),
     "nerf_default_config": (ctypes.c_int, [P(NerfConfig)]),
@@ -79,6 +85,7 @@ SIGNATURES = {
     "nerf_profile_read": (ctypes.c_int, [vp, vp, vp, vp, i32, P(i32)]),
     "nerf_launch_count": (i64, [vp]),
     "nerf_flush_l2": (ctypes.c_int, [vp]),
+    "nerf_log_metrics": (ctypes.c_int, [vp, P(NerfMetrics)]),
     "nerf_debug_plan": (ctypes.c_int, [P(NerfConfig), i32, vp, P(i32), vp, P(i32), vp, P(i32), vp, P(i32), P(i32)]),
     "nerf_debug_plan_biases": (ctypes.c_int, [P(NerfConfig), vp, P(i32)]),
     "nerf_debug_trace": (ctypes.c_int, [vp, i32, vp]),

@@ -245,6 +245,29 @@ class NeRF:
         _check(self.h, self.lib.nerf_render_sharded(self.h, yaw, pitch, 1 if randomize else 0, seed, _ptr(rgba), _ptr(pk)))
         return (rgba, pk) if packed else rgba
 
+    def log_metrics(self, densities=True, prediction=True):
+        """The per-batch TensorBoard projections of src/logging.rs + draw_predictions (display.rs:96-110), computed on the
+        device from the resident batch. Returns a dict: screen_x/screen_y/t (f64 counts, log_screen_coords :13-25,
+        log_query_distances :27-39), world_yx/zx/yz (u32 [100,100], log_query_points_as_maps :41-107), and after predict()
+        density_x/y/z (f64 [2000], log_densities :109-134), density_yx/zx/yz (log_density_maps :136-195), prediction [H,W]."""
+        w, h = self.cfg.image_w, self.cfg.image_h
+        out = {"screen_x": np.empty(w, np.float64), "screen_y": np.empty(h, np.float64), "t": np.empty(2000, np.float64)}
+        for k in ("world_yx", "world_zx", "world_yz"):
+            out[k] = np.empty((100, 100), np.uint32)
+        if densities:
+            for k in ("density_x", "density_y", "density_z"):
+                out[k] = np.empty(2000, np.float64)
+            for k in ("density_yx", "density_zx", "density_yz"):
+                out[k] = np.empty((100, 100), np.uint32)
+        if prediction:
+            out["prediction"] = np.empty((h, w), np.uint32)
+        m = _lib.NerfMetrics()
+        for name, _ in _lib.NerfMetrics._fields_:
+            key = "t" if name == "t_hist" else name
+            setattr(m, name, out[key].ctypes.data if key in out else None)
+        _check(self.h, self.lib.nerf_log_metrics(self.h, ctypes.byref(m)))
+        return out
+
     def train_iter(self, seed):
         _check(self.h, self.lib.nerf_train_iter(self.h, seed))
 

@@ -136,6 +136,7 @@ struct nerf_ctx {
     size_t flush_bytes = 0;
     float *d_frame_rgba = nullptr;       // full-frame render targets (lazily allocated)
     uint32_t *d_frame_0rgb = nullptr;
+    uint8_t *d_metrics = nullptr;        // scratch of nerf_log_metrics (lazily allocated)
 };
 
 namespace {
@@ -561,7 +562,7 @@ int nerf_destroy(nerf_ctx *c) {
     void *ptrs[] = {c->d_params, c->d_grads, c->d_m, c->d_v, c->d_images, c->d_poses, c->d_render_pose, c->d_pix, c->d_view_pick,
                     c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
                     c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
-                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1], c->d_images_u8};
+                    c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1], c->d_images_u8, c->d_metrics};
     for (void *p : ptrs) cudaFree(p);
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_i32) cudaFreeHost(c->h_i32);
@@ -1003,6 +1004,73 @@ int nerf_render_sharded(nerf_ctx *c, float yaw, float pitch, int32_t randomize, 
     if (out_0rgb) CU(c, cudaMemcpyAsync(out_0rgb, c->d_frame_0rgb, sizeof(uint32_t) * (size_t)W * H, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return check_launch(c, "render_sharded");
+}
+
+int nerf_log_metrics(nerf_ctx *c, const nerf_metrics *m) {
+    if (!c || !m) return NERF_ERR_INVALID_ARG;
+    CU(c, cudaSetDevice(c->device));
+    if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "log_metrics: no batch (call nerf_get_batch first)");
+    const bool want_density = m->density_x || m->density_y || m->density_z || m->density_yx || m->density_zx || m->density_yz;
+    if ((want_density || m->prediction) && !c->predicted)
+        return fail(c, NERF_ERR_STATE, "log_metrics: densities / predictions need nerf_predict on this batch");
+    if (c->fwd_deferred) return fail(c, NERF_ERR_STATE, "log_metrics: the forward of this batch is deferred to nerf_step");
+    if (!c->points_valid && !c->batch_poses) return fail(c, NERF_ERR_STATE, "log_metrics: batch has neither points nor ray records");
+    const int W = c->cfg.image_w, H = c->cfg.image_h;
+    // scratch layout (device): screen[W+H] u32 | t[2000] u32 | world[30000] u32 | pad | density_hist[6000] f64 | density keys[30000] u64 | prediction keys[W*H] u64 | resolved u32 [30000 + W*H]
+    const size_t n_u32 = (size_t)W + H + 2000 + 30000;
+    const size_t off_f64 = (n_u32 * 4 + 7) / 8 * 8;
+    const size_t off_dkeys = off_f64 + 6000 * 8;
+    const size_t off_pkeys = off_dkeys + 30000 * 8;
+    const size_t off_res = off_pkeys + (size_t)W * H * 8;
+    const size_t total = off_res + (30000 + (size_t)W * H) * 4;
+    if (!c->d_metrics) CU(c, cudaMalloc(&c->d_metrics, total));
+    uint8_t *base = c->d_metrics;
+    CU(c, cudaMemsetAsync(base, 0, off_res, c->stream));
+    MetricsArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pix_yx = c->d_pix; a.rays = c->d_rays; a.poses = c->batch_poses; a.t = c->d_t;
+    a.points = c->points_valid ? c->d_points : nullptr;
+    a.sigma = want_density ? c->d_sigma : nullptr;
+    a.pixels = m->prediction ? c->d_out : nullptr;
+    a.num_rays = c->R; a.num_samples = c->S; a.img_w = W; a.img_h = H;
+    unsigned int *u32 = reinterpret_cast<unsigned int *>(base);
+    a.screen_hist = u32;
+    a.t_hist = u32 + W + H;
+    a.world_maps = u32 + W + H + 2000;
+    a.density_hist = want_density ? reinterpret_cast<double *>(base + off_f64) : nullptr;
+    a.density_maps = want_density ? reinterpret_cast<unsigned long long *>(base + off_dkeys) : nullptr;
+    a.prediction = m->prediction ? reinterpret_cast<unsigned long long *>(base + off_pkeys) : nullptr;
+    uint32_t *res = reinterpret_cast<uint32_t *>(base + off_res);
+    {
+        Scope s(c, "metrics", 2);
+        launch_metrics(a, c->num_sms, c->stream);
+        launch_metrics_resolve(reinterpret_cast<unsigned long long *>(base + off_dkeys), res, 30000 + (m->prediction ? (int64_t)W * H : 0), c->stream);
+    }
+    int rc = check_launch(c, "metrics");
+    if (rc) return rc;
+    std::vector<uint32_t> h((size_t)W + H + 2000);
+    CU(c, cudaMemcpyAsync(h.data(), u32, h.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    auto d2h = [&](void *dst, const void *src, size_t bytes) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream) : cudaSuccess;
+    };
+    CU(c, d2h(m->world_yx, a.world_maps, 40000));
+    CU(c, d2h(m->world_zx, a.world_maps + 10000, 40000));
+    CU(c, d2h(m->world_yz, a.world_maps + 20000, 40000));
+    if (want_density) {
+        CU(c, d2h(m->density_x, a.density_hist, 16000));
+        CU(c, d2h(m->density_y, a.density_hist + 2000, 16000));
+        CU(c, d2h(m->density_z, a.density_hist + 4000, 16000));
+        CU(c, d2h(m->density_yx, res, 40000));
+        CU(c, d2h(m->density_zx, res + 10000, 40000));
+        CU(c, d2h(m->density_yz, res + 20000, 40000));
+    }
+    if (m->prediction) CU(c, d2h(m->prediction, res + 30000, (size_t)W * H * 4));
+    CU(c, cudaStreamSynchronize(c->stream));
+    // the reference accumulates its counts in f64 (logging.rs:14-15, 32)
+    if (m->screen_x) for (int i = 0; i < W; ++i) m->screen_x[i] = (double)h[i];
+    if (m->screen_y) for (int i = 0; i < H; ++i) m->screen_y[i] = (double)h[(size_t)W + i];
+    if (m->t_hist) for (int i = 0; i < 2000; ++i) m->t_hist[i] = (double)h[(size_t)W + H + i];
+    return NERF_OK;
 }
 
 int nerf_comm_unique_id(void *id128) {

@@ -60,6 +60,26 @@ int launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st); 
 void launch_fill_uniform(float *p, int64_t n, uint32_t seed, float lo, float hi, cudaStream_t st);   // synthetic inputs for stage timing
 void launch_loss_reduce(const float *ray_loss, int n, float inv_count, float *loss_out, cudaStream_t st);
 
+// ---------------------------------------------------------------- metrics.cu
+struct MetricsArgs {
+    const int32_t *pix_yx;     // [R][2]
+    const RayRec *rays;        // [R]
+    const ViewPose *poses;
+    const float *t;            // [R][S]
+    const float *points;       // [R][S][3] or NULL -> rebuilt from the ray records
+    const float *sigma;        // [R][S] or NULL (no density outputs)
+    const float *pixels;       // [R][4] or NULL (no prediction back buffer)
+    int32_t num_rays, num_samples, img_w, img_h;
+    unsigned int *screen_hist;            // [img_w + img_h] or NULL
+    unsigned int *t_hist;                 // [2000] or NULL
+    uint32_t *world_maps;                 // [3][100*100] or NULL
+    double *density_hist;                 // [3][2000] (x, y, z) or NULL
+    unsigned long long *density_maps;     // [3][100*100] keys or NULL
+    unsigned long long *prediction;       // [img_h*img_w] keys or NULL
+};
+void launch_metrics(const MetricsArgs &a, int num_sms, cudaStream_t st);
+void launch_metrics_resolve(const unsigned long long *keys, uint32_t *out, int64_t n, cudaStream_t st);
+
 // ---------------------------------------------------------------- adam.cu
 struct AdamArgs {
     float *p, *m, *v, *g;
