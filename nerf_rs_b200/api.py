@@ -152,14 +152,28 @@ class NeRF:
         m, v = _f32(m), _f32(v)
         _check(self.h, self.lib.nerf_set_adam_state(self.h, _ptr(m), _ptr(v), m.size, step))
 
-    def save(self, path):
-        """NeRF::save (model.rs:211-213). Flat f32 blobs; unlike the reference the Adam
-        state travels too (the .ot file loses it)."""
+    def save(self, path, with_adam=True):
+        """NeRF::save (model.rs:211-213). `*.ot` writes a tch VarStore checkpoint the reference can load (checkpoint.py);
+        anything else a flat .npz. Unlike the reference the Adam state travels too (the .ot file loses it)."""
         m, v, step = self.get_adam_state()
+        if str(path).endswith(".ot"):
+            from . import checkpoint
+            checkpoint.save_varstore(path, self.get_weights(), checkpoint.layer_dims(self.cfg), adam=(m, v, step) if with_adam else None)
+            return
         np.savez(path, weights=self.get_weights(), adam_m=m, adam_v=v, step=np.int64(step))
 
     def load(self, path):
-        """NeRF::load (model.rs:215-217)."""
+        """NeRF::load (model.rs:215-217): a tch `.ot` VarStore file (as written by the reference or by save()) or the .npz."""
+        if str(path).endswith(".ot"):
+            from . import checkpoint
+            try:
+                flat, adam = checkpoint.load_varstore(path, checkpoint.layer_dims(self.cfg))
+            except ValueError as e:
+                raise NerfError(_lib.ERR_INVALID_ARG, str(e))
+            self.set_weights(flat)
+            if adam is not None:
+                self.set_adam_state(*adam)
+            return
         z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
         self.set_weights(z["weights"])
         self.set_adam_state(z["adam_m"], z["adam_v"], int(z["step"]))
