@@ -137,6 +137,12 @@ struct nerf_ctx {
     float *d_frame_rgba = nullptr;       // full-frame render targets (lazily allocated)
     uint32_t *d_frame_0rgb = nullptr;
     uint8_t *d_metrics = nullptr;        // scratch of nerf_log_metrics (lazily allocated)
+    // nerf_predict_points: the host->device copy of the points overlaps the forward kernel (chunked copy on its own stream)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_dirs = nullptr, ev_all = nullptr;
+    unsigned int *d_h2d_flag = nullptr, *h_h2d_seq = nullptr;   // device counter; pinned 1, 2, 3, ... source values
+    const unsigned int *h2d_flag_active = nullptr;               // non-NULL while the resident points are still arriving
+    int64_t h2d_chunk_samples = 0;
 };
 
 namespace {
@@ -280,7 +286,8 @@ int mlp_forward(nerf_ctx *c, int r0, int nr, int train) {
         int rc = ensure_packed(c);
         if (rc) return rc;
         Scope s(c, train ? "mlp_fwd_train" : "mlp_fwd");
-        const TcRayInputs fused{c->d_rays + r0, c->d_t + s0, c->batch_poses};
+        TcRayInputs fused{c->d_rays + r0, c->d_t + s0, c->batch_poses, nullptr, 0};
+        if (c->h2d_flag_active && r0 == 0 && nr == c->R) { fused.h2d_flag = c->h2d_flag_active; fused.h2d_chunk_samples = c->h2d_chunk_samples; }
         if (tc_forward(c->tc, c->points_valid ? c->d_points + 3 * s0 : nullptr, c->d_dirs + 3 * (int64_t)r0, n, c->S, train,
                        c->d_sigma + s0, c->d_rgba + 4 * s0, c->stream, &fused))
             return fail(c, NERF_ERR_INVALID_ARG, tc_last_error(c->tc));
@@ -323,7 +330,7 @@ int composite_forward(nerf_ctx *c, int nr, float *out) {
     return check_launch(c, "composite_fwd");
 }
 
-int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool skip_composite = false) {
+int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool skip_composite = false, bool forward_done = false) {
     if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "predict: no batch (call nerf_get_batch or nerf_predict_points)");
     c->acts_valid = false;
     c->fwd_deferred = false;
@@ -334,12 +341,16 @@ int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool s
         c->predicted = true;
         return NERF_OK;
     }
-    for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
-        const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
-        const int keep = train && c->chunk >= c->R;
-        int rc = mlp_forward(c, r0, nr, keep);
-        if (rc) return rc;
-        if (keep) c->acts_valid = true;
+    if (forward_done) {   // (nerf_predict_points already ran the single-launch forward under its overlapped host copy)
+        if (train) c->acts_valid = true;
+    } else {
+        for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
+            const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
+            const int keep = train && c->chunk >= c->R;
+            int rc = mlp_forward(c, r0, nr, keep);
+            if (rc) return rc;
+            if (keep) c->acts_valid = true;
+        }
     }
     // (a fused training iteration gets its pixels from the compositing backward kernel, which recomputes them)
     int rc = skip_composite ? NERF_OK : composite_forward(c, c->R, c->d_out);
@@ -564,6 +575,13 @@ int nerf_destroy(nerf_ctx *c) {
                     c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
                     c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1], c->d_images_u8, c->d_metrics};
     for (void *p : ptrs) cudaFree(p);
+    if (c->copy_stream) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamDestroy(c->copy_stream);
+        cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_dirs); cudaEventDestroy(c->ev_all);
+        cudaFree(c->d_h2d_flag);
+        cudaFreeHost(c->h_h2d_seq);
+    }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_i32) cudaFreeHost(c->h_i32);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -852,13 +870,55 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
     if (n_points_floats != c->B * 3) return fail(c, NERF_ERR_INVALID_ARG, "predict: query_points must hold num_rays*num_samples*3 floats (model.rs:162)");
     if (n_distances != c->B) return fail(c, NERF_ERR_INVALID_ARG, "predict: distances must hold num_rays*num_samples floats (model.rs:163)");
     if (c->g.Cd && !dirs) return fail(c, NERF_ERR_INVALID_ARG, "predict: this configuration needs ray directions [num_rays*3]");
-    CU(c, cudaMemcpyAsync(c->d_points, query_points, sizeof(float) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->stream));
-    if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->stream));
     c->points_valid = true;
     c->batch_valid = true;
     c->predicted = false;
-    return do_predict(c, train, out_rgba, out_sigma);
+    // The CTA-pair kernel can start on the first tiles while the rest of the points are still crossing PCIe: the copy runs in
+    // kChunks pieces on its own stream, each followed by a 4-byte counter update the kernel's prologue polls. (One launch only:
+    // micro-batched batches, the v1 kernel and the SIMT cross-check take the plain copy-then-run path.)
+    constexpr int kChunks = 8;
+    const bool overlap = c->tc && tc_version(c->tc) == 2 && c->chunk >= c->R && c->R >= 4 * kChunks && !getenv("NERF_B200_NO_H2D_OVERLAP");
+    if (!overlap) {
+        CU(c, cudaMemcpyAsync(c->d_points, query_points, sizeof(float) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->stream));
+        if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->stream));
+        return do_predict(c, train, out_rgba, out_sigma);
+    }
+    if (!c->copy_stream) {
+        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CU(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_all, cudaEventDisableTiming));
+        CU(c, cudaMalloc(&c->d_h2d_flag, sizeof(unsigned int)));
+        CU(c, cudaMallocHost(&c->h_h2d_seq, sizeof(unsigned int) * kChunks));
+        for (int k = 0; k < kChunks; ++k) c->h_h2d_seq[k] = (unsigned int)k + 1u;
+    }
+    // everything enqueued so far (earlier readers of these buffers, the counter reset) precedes the copies
+    CU(c, cudaMemsetAsync(c->d_h2d_flag, 0, sizeof(unsigned int), c->stream));
+    CU(c, cudaEventRecord(c->ev_main, c->stream));
+    CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
+    if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(c, cudaEventRecord(c->ev_dirs, c->copy_stream));
+    const int rays_per_chunk = (c->R + kChunks - 1) / kChunks;
+    const int64_t chunk_samples = (int64_t)rays_per_chunk * c->S;
+    for (int k = 0; k < kChunks; ++k) {
+        const int64_t s0 = (int64_t)k * chunk_samples;
+        const int64_t ns = (c->B - s0 < chunk_samples) ? c->B - s0 : chunk_samples;
+        if (ns > 0) CU(c, cudaMemcpyAsync(c->d_points + 3 * s0, query_points + 3 * s0, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->d_h2d_flag, c->h_h2d_seq + k, sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->copy_stream));   // compositing only
+    CU(c, cudaEventRecord(c->ev_all, c->copy_stream));
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_dirs, 0));
+    c->h2d_flag_active = c->d_h2d_flag;
+    c->h2d_chunk_samples = chunk_samples;
+    int rc = ensure_packed(c);
+    if (rc == NERF_OK) rc = mlp_forward(c, 0, c->R, train ? 1 : 0);
+    c->h2d_flag_active = nullptr;
+    cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_all, 0);   // (also on the error path: later work must not race the copies)
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(c, NERF_ERR_CUDA, cudaGetErrorString(e));
+    return do_predict(c, train, out_rgba, out_sigma, false, /*forward_done=*/true);
 }
 
 int nerf_compositing(nerf_ctx *c, const float *densities, const float *colors, const float *distances, int32_t num_rays,

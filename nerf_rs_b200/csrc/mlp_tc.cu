@@ -925,6 +925,8 @@ int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, in
         if (!points) {
             if (!fused) { s->err = "tc_forward: neither points nor ray inputs"; return -1; }
             l.rays = fused->rays; l.t = fused->t; l.poses = fused->poses;
+        } else if (fused && fused->h2d_flag) {
+            l.h2d_flag = fused->h2d_flag; l.h2d_chunk_samples = fused->h2d_chunk_samples;
         }
         l.save_base = train ? s->d_act : nullptr; l.save_slots = s->plan.act_slots;
         l.mask_base = s->d_mask; l.mask_slots = s->plan.mask_slots;

@@ -181,6 +181,8 @@ struct Chain2Launch {
     int32_t mask_slots;
     int32_t wide, e_slot, mask_words;
     unsigned long long *trace;   // debug: [3][2048][4] clock64 stamps of CTA 0, or NULL
+    const unsigned int *h2d_flag;   // points still arriving from the host: sample gs may be read once *h2d_flag > gs / h2d_chunk_samples
+    int64_t h2d_chunk_samples;
 };
 void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st);
 int tc2_bias_upload(const void *owner, uint64_t version, const float *d_bias, int n_floats, cudaStream_t st);
@@ -201,6 +203,10 @@ struct TcRayInputs {
     const RayRec *rays;
     const float *t;
     const ViewPose *poses;
+    // caller-supplied points that are still being copied from the host on another stream (nerf_predict_points): the copy
+    // stream bumps *h2d_flag after every chunk of h2d_chunk_samples samples; NULL = everything is already resident
+    const unsigned int *h2d_flag;
+    int64_t h2d_chunk_samples;
 };
 int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, int S, int train, float *sigma, float *rgba,
                cudaStream_t st, const TcRayInputs *fused = nullptr);

@@ -88,6 +88,8 @@ struct Chain2Args {
     uint32_t *mask_base;
     int32_t mask_slots;
     unsigned long long *trace;   // debug: [3 roles][kTraceEvents][4] clock64 stamps of CTA 0, or NULL
+    const unsigned int *h2d_flag;   // caller-supplied points still arriving from the host (see Chain2Launch), or NULL
+    int64_t h2d_chunk_samples;
 };
 constexpr int kTraceEvents = 2048;
 __device__ __forceinline__ void trace4(const Chain2Args &a, int role, int idx, unsigned long long t0, unsigned long long t1,
@@ -443,7 +445,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                 float v[3] = {0.f, 0.f, 0.f};
                 if (valid) {
                     if (a.points) {
-                        v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2];
+                        if (a.h2d_flag) {
+                            // the host->device copy of the points runs on another stream, chunk by chunk: wait until the chunk
+                            // holding this sample has landed (the copy engine writes the counter after the chunk, in stream order)
+                            const unsigned int need = (unsigned int)(gs / a.h2d_chunk_samples) + 1u;
+                            unsigned int spins = 0;
+                            while (*reinterpret_cast<const volatile unsigned int *>(a.h2d_flag) < need) {
+                                __nanosleep(256);
+                                if (++spins > (1u << 24)) { printf("nerf_b200: host copy never arrived (chunk %u)\n", need); __trap(); }
+                            }
+                            v[0] = __ldcg(a.points + 3 * gs); v[1] = __ldcg(a.points + 3 * gs + 1); v[2] = __ldcg(a.points + 3 * gs + 2);
+                        } else {
+                            v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2];
+                        }
                     } else {
                         // fused sampling: the point never exists in HBM -- same ops as k_sample, bit for bit
                         const RayRec rec = a.rays[gs / a.S];
@@ -707,6 +721,7 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
     a.points = l.points; a.rays = l.rays; a.t = l.t; a.poses = l.poses; a.dirs = l.dirs; a.sigma = l.sigma; a.rgba = l.rgba; a.d_sigma = l.d_sigma; a.d_rgba = l.d_rgba;
     a.save_base = l.save_base; a.save_slots = l.save_slots; a.mask_base = l.mask_base; a.mask_slots = l.mask_slots;
     a.trace = l.trace;
+    a.h2d_flag = l.h2d_flag; a.h2d_chunk_samples = l.h2d_chunk_samples;
     a.wide = l.wide; a.e_slot = l.e_slot; a.mask_words = l.mask_words;
     const int max_clusters = l.num_sms / 2;
     const int clusters = a.n_pairs < max_clusters ? a.n_pairs : max_clusters;
