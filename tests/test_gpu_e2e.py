@@ -150,3 +150,27 @@ def test_micro_batched_train_iter_equals_single_launch():
         res.append((m.last_loss(), m.get_grads()))
     assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[0][0])
     assert np.allclose(res[0][1], res[1][1], rtol=1e-3, atol=1e-6 * np.abs(res[0][1]).max())
+
+
+def test_overlapped_host_copy_equals_plain_copy():
+    """nerf_predict_points streams the points in 8 chunks on a second stream while the forward kernel already runs (its prologue
+    polls the copy engine's counter): same bits as copy-then-run, also when rays and tiles do not divide into the chunks."""
+    import os
+    cfg = nb.default_config(image_w=64, image_h=64, num_rays=100, num_samples=50, hidden=128)   # 5000 samples: 39.06 tiles, 12.5 rays per chunk
+    pts, t, dirs, gold = G.make_points(100, 50, 9)
+    res = []
+    for plain in (False, True):
+        if plain:
+            os.environ["NERF_B200_NO_H2D_OVERLAP"] = "1"
+        try:
+            m = nb.NeRF(cfg)
+            m.set_weights(M.flatten_params(M.init_params(G.model_cfg(cfg), 0)).numpy())
+            outs = [m.predict(pts * np.float32(1 + 0.01 * k), t, dirs.reshape(-1), train=True) for k in range(3)]   # back-to-back calls reuse the counter
+            loss = nb.Trainer(m).step(outs[-1][0], gold)
+            res.append((outs, loss, m.get_grads()))
+        finally:
+            os.environ.pop("NERF_B200_NO_H2D_OVERLAP", None)
+    for (oa, sa), (ob, sb) in zip(res[0][0], res[1][0]):
+        assert np.array_equal(oa, ob) and np.array_equal(sa, sb)
+    assert res[0][1] == res[1][1]
+    assert np.allclose(res[0][2], res[1][2], rtol=1e-3, atol=1e-6 * np.abs(res[1][2]).max())   # (wgrad atomics are unordered)
