@@ -190,8 +190,8 @@ int64_t nerf_launch_count(const nerf_ctx *ctx);  /* kernels launched by this con
 int nerf_flush_l2(nerf_ctx *ctx);                /* overwrite a >L2-sized scratch buffer */
 
 /* ---- per-batch logging projections (src/logging.rs, src/display.rs:96-110) computed on the device from the resident batch.
- * Every pointer is a caller-owned HOST buffer or NULL to skip that output. Density outputs and `prediction` need a
- * preceding nerf_predict* on the batch (NERF_ERR_STATE otherwise). */
+ * Every pointer is a caller-owned HOST buffer or NULL to skip that output. Density outputs and `prediction` need the
+ * batch's forward to have run: nerf_predict*, or a completed nerf_step / nerf_train_iter (NERF_ERR_STATE otherwise). */
 typedef struct nerf_metrics {
     double *screen_x;        /* [image_w]  log_screen_coords (logging.rs:13-25): counts of indices[r][0] -- the reference binds `[x, y]` to the stored [y, x] pair */
     double *screen_y;        /* [image_h]  counts of indices[r][1] */

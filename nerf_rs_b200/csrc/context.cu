@@ -117,6 +117,7 @@ struct nerf_ctx {
     int32_t *h_i32 = nullptr;  // pinned staging for index conversion
     size_t h_i32_cap = 0;
     bool batch_valid = false, predicted = false, acts_valid = false;
+    bool outputs_valid = false;           // d_sigma / d_out hold the resident batch's densities and pixels (survives nerf_step)
     int gen_pix = 0, gen_view = 0, pick_views = 0;   // Philox picks requested for the next sampler launch
     bool fwd_deferred = false;            // nerf_train_iter on a micro-batched batch: the forward runs inside nerf_step
     bool points_valid = false;            // d_points holds the batch's sample positions (else: fused sampling in the MLP prologue)
@@ -356,6 +357,7 @@ int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool s
     int rc = skip_composite ? NERF_OK : composite_forward(c, c->R, c->d_out);
     if (rc) return rc;
     c->predicted = true;
+    c->outputs_valid = !skip_composite;
     if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_out, sizeof(float) * 4 * c->R, cudaMemcpyDeviceToHost, c->stream));
     if (out_sigma) CU(c, cudaMemcpyAsync(out_sigma, c->d_sigma, sizeof(float) * c->B, cudaMemcpyDeviceToHost, c->stream));
     if (out_rgba || out_sigma) CU(c, cudaStreamSynchronize(c->stream));
@@ -426,6 +428,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     c->acts_valid = false;
     c->predicted = false;
     c->fwd_deferred = false;
+    c->outputs_valid = true;   // the compositing backward wrote the pixels, every micro-batch's forward the densities
     if (nranks > 1 && !p2p) {
         Scope s(c, "grad_allreduce");
         char eb[256] = {0};
@@ -839,6 +842,7 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
     if (rc) return rc;
     c->batch_valid = true;
     c->predicted = false;
+    c->outputs_valid = false;
     c->acts_valid = false;
     bool sync = false;
     if (out_points) { CU(c, cudaMemcpyAsync(out_points, c->d_points, sizeof(float) * 3 * c->B, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
@@ -873,6 +877,7 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
     c->points_valid = true;
     c->batch_valid = true;
     c->predicted = false;
+    c->outputs_valid = false;
     // The CTA-pair kernel can start on the first tiles while the rest of the points are still crossing PCIe: the copy runs in
     // kChunks pieces on its own stream, each followed by a 4-byte counter update the kernel's prologue polls. (One launch only:
     // micro-batched batches, the v1 kernel and the SIMT cross-check take the plain copy-then-run path.)
@@ -998,6 +1003,7 @@ static int render_rows_device(nerf_ctx *c, float yaw, float pitch, int32_t y0, i
     const int64_t total = (int64_t)(y1 - y0) * W;
     c->batch_valid = false;
     c->predicted = false;
+    c->outputs_valid = false;
     c->acts_valid = false;
     const int saveR = c->R;
     int rc = NERF_OK;
@@ -1071,9 +1077,8 @@ int nerf_log_metrics(nerf_ctx *c, const nerf_metrics *m) {
     CU(c, cudaSetDevice(c->device));
     if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "log_metrics: no batch (call nerf_get_batch first)");
     const bool want_density = m->density_x || m->density_y || m->density_z || m->density_yx || m->density_zx || m->density_yz;
-    if ((want_density || m->prediction) && !c->predicted)
-        return fail(c, NERF_ERR_STATE, "log_metrics: densities / predictions need nerf_predict on this batch");
-    if (c->fwd_deferred) return fail(c, NERF_ERR_STATE, "log_metrics: the forward of this batch is deferred to nerf_step");
+    if ((want_density || m->prediction) && !c->outputs_valid)
+        return fail(c, NERF_ERR_STATE, "log_metrics: densities / predictions need nerf_predict (or a completed nerf_step / nerf_train_iter) on this batch");
     if (!c->points_valid && !c->batch_poses) return fail(c, NERF_ERR_STATE, "log_metrics: batch has neither points nor ray records");
     const int W = c->cfg.image_w, H = c->cfg.image_h;
     // scratch layout (device): screen[W+H] u32 | t[2000] u32 | world[30000] u32 | pad | density_hist[6000] f64 | density keys[30000] u64 | prediction keys[W*H] u64 | resolved u32 [30000 + W*H]

@@ -70,3 +70,8 @@ def test_metrics_need_a_batch_and_a_prediction():
     with pytest.raises(nb.NerfError):
         m.log_metrics()                                # densities requested before predict
     assert m.log_metrics(densities=False, prediction=False)["t"].sum() == 64 * 16
+    rng = np.random.default_rng(0)
+    m.set_images(rng.random((4, 64 * 64, 4), dtype=np.float32))
+    m.train_iter(3)                                    # fused iteration: the batch, its densities and pixels stay resident
+    got = m.log_metrics()
+    assert got["t"].sum() == 64 * 16 and np.count_nonzero(got["prediction"]) > 0 and np.isfinite(got["density_x"]).all()
