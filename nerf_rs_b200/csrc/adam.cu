@@ -14,6 +14,8 @@
 namespace {
 
 __global__ void __launch_bounds__(256) k_adam(AdamArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t n4 = a.n >> 2;
     const float omb1 = 1.f - a.beta1, omb2 = 1.f - a.beta2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -66,6 +68,8 @@ __device__ __forceinline__ float4 ld_peer_f4(const float *p) {   // peer memory:
 }
 
 __global__ void __launch_bounds__(256) k_adam_p2p(const __grid_constant__ AdamP2PArgs a) {
+    pdl_trigger();
+    pdl_wait();
     // 1. publish "my gradient for `step` is complete" (the weight-gradient kernel precedes this one in the stream) in
     //    every rank's flag array, slot = my rank
     if (blockIdx.x == 0 && (int)threadIdx.x < a.nranks) {
@@ -154,7 +158,7 @@ void launch_adam(const AdamArgs &a, int num_sms, cudaStream_t st) {
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > num_sms * 8) blocks = num_sms * 8;
     if (blocks < 1) blocks = 1;
-    k_adam<<<blocks, 256, 0, st>>>(a);
+    launch_pdl(k_adam, dim3(blocks), dim3(256), 0, st, a);
 }
 
 void launch_adam_p2p(const AdamP2PArgs &a, int num_sms, cudaStream_t st) {
@@ -162,7 +166,7 @@ void launch_adam_p2p(const AdamP2PArgs &a, int num_sms, cudaStream_t st) {
     int blocks = (int)((n4 + 255) / 256);
     if (blocks > num_sms * 4) blocks = num_sms * 4;
     if (blocks < 1) blocks = 1;
-    k_adam_p2p<<<blocks, 256, 0, st>>>(a);
+    launch_pdl(k_adam_p2p, dim3(blocks), dim3(256), 0, st, a);
 }
 
 void launch_init_uniform(float *p, const NetGeom &g, uint64_t seed, cudaStream_t st) {

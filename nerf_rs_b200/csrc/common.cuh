@@ -63,6 +63,33 @@ __host__ __device__ inline float philox_uniform(uint64_t seed, uint32_t stream, 
     return (float)(c[0] >> 8) * (1.0f / 16777216.0f);
 }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------
+// The kernels of a training step are launched with the programmatic-stream-serialization attribute: a kernel announces
+// at its very start that its successor may begin (pdl_trigger), the successor's CTAs become resident as SMs free up and run
+// their private prologue (barrier init, TMEM allocation, table loads), and only then wait for the predecessor grid to have
+// completed and flushed (pdl_wait) before touching anything it wrote. NERF_B200_NO_PDL=1 launches plainly (A/B).
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    static const bool off = getenv("NERF_B200_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 #define NERF_STREAM_PIX_Y 0u
 #define NERF_STREAM_PIX_X 1u
 #define NERF_STREAM_VIEW 2u

@@ -40,6 +40,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <bool kBackward, int SPL>
 __global__ void __launch_bounds__(kWarps * 32)
 k_composite(CompositeArgs a) {
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = a.num_samples;
     float loss_sum = 0.f;   // this warp's squared errors, rays in loop order (identical in every lane)
@@ -186,7 +188,7 @@ int launch_composite_spl(CompositeArgs a, int num_sms, cudaStream_t st) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     a.loss_partials_total = a.loss_partials_prior + blocks;
-    k_composite<kBackward, SPL><<<blocks, kWarps * 32, 0, st>>>(a);
+    launch_pdl(k_composite<kBackward, SPL>, dim3(blocks), dim3(kWarps * 32), 0, st, a);
     return blocks;
 }
 template <bool kBackward>

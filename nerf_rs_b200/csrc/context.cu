@@ -401,17 +401,17 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         loss_partials_done += launch_composite_bwd(a, c->num_sms, c->stream);
         return check_launch(c, "composite_bwd");
     };
-    int rc = NERF_OK;
-    if (!c->fwd_deferred) {
-        rc = composite_backward(0, c->R);
-        if (rc) return rc;
-    }
     // gradients accumulate (+=) over micro-batches and weight-gradient CTAs: start from zero.
     // With the peer-memory all-reduce the local gradient goes to one of two buffers the other ranks read directly; a
     // buffer is reused two steps later, after every peer has passed the next step's hand-shake.
     const bool p2p = nranks > 1 && c->comm.p2p;
     float *gacc = p2p ? c->d_gacc[(c->comm.p2p_step + 1) & 1] : c->d_grads;
-    CU(c, cudaMemsetAsync(gacc, 0, sizeof(float) * c->g.n_params, c->stream));
+    CU(c, cudaMemsetAsync(gacc, 0, sizeof(float) * c->g.n_params, c->stream));   // (before the kernels, so that they stay back to back for the programmatic launches)
+    int rc = NERF_OK;
+    if (!c->fwd_deferred) {
+        rc = composite_backward(0, c->R);
+        if (rc) return rc;
+    }
     for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
         const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
         if (!c->acts_valid) {

@@ -490,7 +490,8 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     float *s_sg = s_bias + 256;     // sigma-row slice (256) + its bias (1)
     float *s_dsg = s_sg + 260;      // [stage][64] d(sigma) of the stage's sample rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const WgradWork wk = a.work[blockIdx.x];
+    pdl_trigger();
+    const WgradWork wk = a.work[blockIdx.x];     // (uploaded by the host before the launch, not produced by the predecessor)
     if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x] = global_ns();
     if (wk.n_seg <= 0) return;  // uniform per CTA
 
@@ -508,6 +509,7 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();   // the dgrad kernel's panels (and the zeroed gradient buffer) are complete from here on
 
     // A CTA works through up to kWgMaxSeg segments = (unit, tile range) pieces, so the 148 CTAs can split the units' total
     // cost evenly instead of in whole CTAs per unit. Ring stage / phase counters simply run on across segments (every role
@@ -731,6 +733,8 @@ __global__ void k_pack_chunks(const PackChunk *chunks, const float *__restrict__
 __global__ void k_pack_all(const PackChunk *fwd_chunks, int n_fwd, uint8_t *__restrict__ fwd_dst, const PackChunk *bwd_chunks, int n_bwd,
                            uint8_t *__restrict__ bwd_dst, const PackBias *pb, int n_bias, const float *__restrict__ params,
                            float *__restrict__ bias_dst) {
+    pdl_trigger();
+    pdl_wait();
     const int b = blockIdx.x;
     if (b >= n_fwd + n_bwd) {
         const PackBias e = pb[b - n_fwd - n_bwd];
@@ -899,7 +903,7 @@ const char *tc_last_error(const TcState *s) { return s->err.c_str(); }
 
 void tc_pack_weights(TcState *s, const float *params, cudaStream_t st) {
     const int nb = (int)s->plan.biases.size();
-    k_pack_all<<<s->fwd_train.n_chunks + s->bwd.n_chunks + nb, 256, 0, st>>>(s->fwd_train.chunks, s->fwd_train.n_chunks, s->fwd_train.wpack,
+    launch_pdl(k_pack_all, dim3(s->fwd_train.n_chunks + s->bwd.n_chunks + nb), dim3(256), 0, st, s->fwd_train.chunks, s->fwd_train.n_chunks, s->fwd_train.wpack,
                                                                               s->bwd.chunks, s->bwd.n_chunks, s->bwd.wpack, s->d_pbias, nb,
                                                                               params, s->d_bias);
     ++s->bias_version;
@@ -1036,7 +1040,7 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
     w.act_base = s->d_act; w.grad_base = s->d_grad;
     w.act_slots = s->plan.act_slots; w.grad_slots = s->plan.grad_slots;
     w.grads = grads;
-    k_wgrad<<<s->num_sms, 256, kWgSmem, st>>>(w);
+    launch_pdl(k_wgrad, dim3(s->num_sms), dim3(256), kWgSmem, st, w);
     if (between) between(user, nullptr);
     return 0;
 }

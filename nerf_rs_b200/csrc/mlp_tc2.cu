@@ -245,6 +245,7 @@ __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uin
 template <bool kBwd, bool kSave, bool kWide>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain2(const __grid_constant__ Chain2Args a) {
     constexpr int kG = kWide ? kMaxGroups : kMaxGroups / 2;   // 32-column groups per column-slice warp (256- vs 512-column jobs)
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t bars = sbase + kSmemBars;
@@ -286,6 +287,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
     ptx::cluster_sync();   // barriers of both CTAs initialised before any remote arrive / multicast commit
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();   // everything above is private to the CTA pair; the predecessor kernel's outputs are read only below
 
     // Register rebalancing (setmaxnreg): the four service warps (producer, MMA issuer / relay, TMEM allocator, store warp)
     // need few registers; the 16 epilogue warps hold 32 accumulator columns, 16 packed words and addressing.
@@ -727,12 +729,12 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
     const int clusters = a.n_pairs < max_clusters ? a.n_pairs : max_clusters;
     const int grid = 2 * clusters;
     if (l.wide) {
-        if (l.bwd) k_chain2<true, true, true><<<grid, kThreads, kChain2Smem, st>>>(a);
-        else if (l.save) k_chain2<false, true, true><<<grid, kThreads, kChain2Smem, st>>>(a);
-        else k_chain2<false, false, true><<<grid, kThreads, kChain2Smem, st>>>(a);
+        if (l.bwd) launch_pdl(k_chain2<true, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else if (l.save) launch_pdl(k_chain2<false, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else launch_pdl(k_chain2<false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
     } else {
-        if (l.bwd) k_chain2<true, true, false><<<grid, kThreads, kChain2Smem, st>>>(a);
-        else if (l.save) k_chain2<false, true, false><<<grid, kThreads, kChain2Smem, st>>>(a);
-        else k_chain2<false, false, false><<<grid, kThreads, kChain2Smem, st>>>(a);
+        if (l.bwd) launch_pdl(k_chain2<true, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else if (l.save) launch_pdl(k_chain2<false, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else launch_pdl(k_chain2<false, false, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
     }
 }

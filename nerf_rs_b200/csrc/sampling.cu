@@ -92,6 +92,8 @@ template <int SPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 k_sample(SampleArgs a) {
     __shared__ float s_p[kWarpsPerBlock][96];
+    pdl_trigger();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = a.num_samples;
     for (int r = blockIdx.x * kWarpsPerBlock + warp; r < a.num_rays; r += gridDim.x * kWarpsPerBlock) {
@@ -246,7 +248,7 @@ static void launch_sample_spl(const SampleArgs &a, int num_sms, cudaStream_t st)
     const int cap = num_sms * (occ < 1 ? 1 : occ);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    k_sample<SPL><<<blocks, kWarpsPerBlock * 32, 0, st>>>(a);
+    launch_pdl(k_sample<SPL>, dim3(blocks), dim3(kWarpsPerBlock * 32), 0, st, a);
 }
 void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st) {
     const int spl = (a.num_samples + 31) / 32;
