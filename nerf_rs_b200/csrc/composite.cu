@@ -205,20 +205,6 @@ int launch_composite_any(const CompositeArgs &a, int num_sms, cudaStream_t st) {
     }
 }
 
-// deterministic fixed-order reduction of per-ray squared errors -> mean loss
-__global__ void k_loss_reduce(const float *__restrict__ ray_loss, int n, float inv_count, float *__restrict__ loss_out) {
-    __shared__ float sh[1024];
-    float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s += ray_loss[i];
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    for (int d = blockDim.x >> 1; d > 0; d >>= 1) {
-        if ((int)threadIdx.x < d) sh[threadIdx.x] += sh[threadIdx.x + d];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *loss_out = sh[0] * inv_count;
-}
-
 // synthetic inputs for nerf_debug_bench_stage: hashed uniforms in [lo, hi)
 __global__ void k_fill_uniform(float *__restrict__ p, int64_t n, uint32_t seed, float lo, float hi) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -236,6 +222,3 @@ void launch_fill_uniform(float *p, int64_t n, uint32_t seed, float lo, float hi,
 }
 void launch_composite_fwd(const CompositeArgs &a, int num_sms, cudaStream_t st) { launch_composite_any<false>(a, num_sms, st); }
 int launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st) { return launch_composite_any<true>(a, num_sms, st); }
-void launch_loss_reduce(const float *ray_loss, int n, float inv_count, float *loss_out, cudaStream_t st) {
-    k_loss_reduce<<<1, 1024, 0, st>>>(ray_loss, n, inv_count, loss_out);
-}

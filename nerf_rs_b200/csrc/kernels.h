@@ -58,7 +58,6 @@ struct CompositeArgs {
 void launch_composite_fwd(const CompositeArgs &a, int num_sms, cudaStream_t st);
 int launch_composite_bwd(const CompositeArgs &a, int num_sms, cudaStream_t st);   // returns the grid size (= partials written)
 void launch_fill_uniform(float *p, int64_t n, uint32_t seed, float lo, float hi, cudaStream_t st);   // synthetic inputs for stage timing
-void launch_loss_reduce(const float *ray_loss, int n, float inv_count, float *loss_out, cudaStream_t st);
 
 // ---------------------------------------------------------------- metrics.cu
 struct MetricsArgs {
