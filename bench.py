@@ -77,6 +77,8 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        if self._run_nvml():
+            return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
@@ -88,6 +90,29 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(0.1)
+
+    def _run_nvml(self):
+        """Same fields through NVML (a query costs ~0.1 ms instead of nvidia-smi's ~0.5 s): one sample every 20 ms."""
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4)]
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons(h)
+        except Exception:
+            return False
+        while not self.stop_flag:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                r = get_reasons(h)
+                self.rows.append([str(sm), str(mx)] + [("Active" if r & b else "Not Active") for _, b in bits])
+            except Exception:
+                pass
+            time.sleep(0.02)
+        return True
 
     def summary(self):
         if not self.rows:
