@@ -57,7 +57,7 @@ struct ChainArgs {
     const float *d_rgba;    // bwd in [n][4]
     uint8_t *save_base;     // per-tile panel area written by this launch (act or grad), or NULL
     int32_t save_slots;
-    uint32_t *mask_base;    // [tile][mask_slots][128][8]
+    uint32_t *mask_base;    // [tile][mask_slots][128][8] (v1 kernel; the CTA-pair kernel stores each tile slot word-major, [8][128])
     int32_t mask_slots;
     unsigned long long *trace;  // debug: [3 roles][kTraceEvents][2] clock64 stamps of CTA 0, or NULL
 };
@@ -1057,7 +1057,17 @@ int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaS
     }
     if (!src) return -1;
     if (cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -2;
-    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -2;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return -2;
+    if (area == 2 && s->version == 2) {
+        // the CTA-pair kernel keeps a tile's masks word-major ([word][row], coalesced warp stores); callers get [row][word]
+        const int nw = s->plan.mask_words;
+        std::vector<uint32_t> tmp((size_t)NERF_TILE_M * nw);
+        memcpy(tmp.data(), out, bytes);
+        uint32_t *o = static_cast<uint32_t *>(out);
+        for (int r = 0; r < NERF_TILE_M; ++r)
+            for (int w = 0; w < nw; ++w) o[(size_t)r * nw + w] = tmp[(size_t)w * NERF_TILE_M + r];
+    }
+    return 0;
 }
 
 // marks of the last k_wgrad launch + the CTA -> (unit, tile range) assignment; out: [num_sms][8] = start, first stage, MMAs

@@ -237,7 +237,7 @@ __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uin
             uint32_t w[16];
             epi_group<kSave, kKind>(r, bias_base + (int)j.bias_off + G * 32, m, w);
             store_group(lane_base, j.out_slot, row, G, w);
-            if (kSave && kKind == EK_RELU && mask_row) mask_row[G] = m;
+            if (kSave && kKind == EK_RELU && mask_row) mask_row[G * NERF_TILE_M] = m;   // [word][row]: a warp writes 128 contiguous bytes
         }
     }
 }
@@ -537,10 +537,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             uint32_t *mask_row = nullptr;
             uint32_t pm[kG];
             if (j.mask_slot >= 0 && j.kind != EK_SIGMA && j.kind != EK_RGBA) {
-                mask_row = a.mask_base + (((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M + row) * a.mask_words;
+                mask_row = a.mask_base + ((size_t)tile * a.mask_slots + j.mask_slot) * NERF_TILE_M * a.mask_words + row;   // word-major: [G][row]
                 if (kBwd && j.kind == EK_DMASK) {   // global loads issued now, consumed after the accumulator wait
 #pragma unroll
-                    for (int g = 0; g < kG; ++g) pm[g] = (G0 + g < G1) ? mask_row[G0 + g] : 0u;
+                    for (int g = 0; g < kG; ++g) pm[g] = (G0 + g < G1) ? mask_row[(G0 + g) * NERF_TILE_M] : 0u;
                 }
             }
             const unsigned long long te1 = a.trace ? clock64() : 0;
