@@ -242,7 +242,9 @@ __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uin
     }
 }
 
-template <bool kBwd, bool kSave, bool kWide>
+// kH2D: the caller's points are still arriving from the host (nerf_predict_points) -- a separate instantiation, because even a
+// never-taken polling branch in the prologue costs the register-starved epilogue 10-25 % (same-box A/B of the two builds).
+template <bool kBwd, bool kSave, bool kWide, bool kH2D = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain2(const __grid_constant__ Chain2Args a) {
     constexpr int kG = kWide ? kMaxGroups : kMaxGroups / 2;   // 32-column groups per column-slice warp (256- vs 512-column jobs)
     pdl_trigger();
@@ -447,14 +449,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                 float v[3] = {0.f, 0.f, 0.f};
                 if (valid) {
                     if (a.points) {
-                        if (a.h2d_flag) {
+                        if (kH2D && a.h2d_flag) {
                             // the host->device copy of the points runs on another stream, chunk by chunk: wait until the chunk
                             // holding this sample has landed (the copy engine writes the counter after the chunk, in stream order)
                             const unsigned int need = (unsigned int)(gs / a.h2d_chunk_samples) + 1u;
                             unsigned int spins = 0;
                             while (*reinterpret_cast<const volatile unsigned int *>(a.h2d_flag) < need) {
                                 __nanosleep(256);
-                                if (++spins > (1u << 24)) { printf("nerf_b200: host copy never arrived (chunk %u)\n", need); __trap(); }
+                                if (++spins > (1u << 24)) __trap();   // the host copy never arrived
                             }
                             v[0] = __ldcg(a.points + 3 * gs); v[1] = __ldcg(a.points + 3 * gs + 1); v[2] = __ldcg(a.points + 3 * gs + 2);
                         } else {
@@ -667,6 +669,10 @@ Lane2Program *tc2_upload(const LaneProgram &p, uint32_t, std::string &err) {
         ok = ok && cudaFuncSetAttribute(k_chain2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(k_chain2<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(k_chain2<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         if (!ok) { err = std::string("tc2: cudaFuncSetAttribute failed: ") + cudaGetErrorString(cudaGetLastError()); return nullptr; }
         attr_done = true;
     }
@@ -730,10 +736,14 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
     const int grid = 2 * clusters;
     if (l.wide) {
         if (l.bwd) launch_pdl(k_chain2<true, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else if (l.h2d_flag && l.save) launch_pdl(k_chain2<false, true, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else if (l.h2d_flag) launch_pdl(k_chain2<false, false, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else if (l.save) launch_pdl(k_chain2<false, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else launch_pdl(k_chain2<false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
     } else {
         if (l.bwd) launch_pdl(k_chain2<true, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else if (l.h2d_flag && l.save) launch_pdl(k_chain2<false, true, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        else if (l.h2d_flag) launch_pdl(k_chain2<false, false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else if (l.save) launch_pdl(k_chain2<false, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else launch_pdl(k_chain2<false, false, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
     }
