@@ -244,10 +244,13 @@ __device__ __forceinline__ void epi_hidden(const LaneJob &j, uint32_t taddr, uin
 
 // kH2D: the caller's points are still arriving from the host (nerf_predict_points) -- a separate instantiation, because even a
 // never-taken polling branch in the prologue costs the register-starved epilogue 10-25 % (same-box A/B of the two builds).
-template <bool kBwd, bool kSave, bool kWide, bool kH2D = false>
+// kTrace: clock64 stamps of CTA 0 for tools/trace_chain2.py -- also its own instantiation, for the same reason (the stamps are
+// 64-bit values that stay live across a whole epilogue step).
+template <bool kBwd, bool kSave, bool kWide, bool kH2D = false, bool kTrace = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain2(const __grid_constant__ Chain2Args a) {
     constexpr int kG = kWide ? kMaxGroups : kMaxGroups / 2;   // 32-column groups per column-slice warp (256- vs 512-column jobs)
     pdl_trigger();
+    const bool tracing = kTrace && a.trace != nullptr;
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = ptx::smem_u32(smem);
     const uint32_t bars = sbase + kSmemBars;
@@ -312,9 +315,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     if (producer) {
                         const uint32_t half = (uint32_t)s_ops[i].n * 64u;   // (n / 2) rows * 128 B
                         const uint8_t *src = a.wpack + s_ops[i].w_off + rank * half;
-                        const unsigned long long tp0 = a.trace ? clock64() : 0;
+                        const unsigned long long tp0 = tracing ? clock64() : 0;
                         ptx::mbar_wait(bar(kBarEmpty + stage), phase ^ 1u);
-                        if (a.trace && lane_id == 0) trace4(a, 2, ev++, tp0, clock64(), 0, 0);
+                        if (tracing && lane_id == 0) trace4(a, 2, ev++, tp0, clock64(), 0, 0);
                         if (ptx::elect_one()) {
                             ptx::mbar_arrive_expect_tx(bar(kBarFullL + stage), half);
                             ptx::bulk_g2s(sbase + kSmemSlots + stage * kStageBytes, src, half, bar(kBarFullL + stage));
@@ -344,17 +347,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                 const bool reuse = shared && ln == 1;
                 const bool release = !shared || ln == 1;
                 if (reuse) { stage = stage0; phase = phase0; }
-                unsigned long long tm0 = a.trace ? clock64() : 0;
+                unsigned long long tm0 = tracing ? clock64() : 0;
                 ptx::mbar_wait_cluster(bar(kBarEpiDone + ln), (done_phase >> ln) & 1u);
                 done_phase ^= 1u << ln;
                 for (int i = gm.op_begin; i < gm.op_end; ++i) {
                     const LaneOp op = s_ops[i];
-                    if (i != gm.op_begin && a.trace) tm0 = clock64();
+                    if (i != gm.op_begin && tracing) tm0 = clock64();
                     if (!reuse) {
                         ptx::mbar_wait(bar(kBarFullL + stage), phase);   // both halves: own bytes + the peer's relay
                     }
                     ptx::tc_fence_after();
-                    const unsigned long long tm1 = a.trace ? clock64() : 0;
+                    const unsigned long long tm1 = tracing ? clock64() : 0;
                     const uint32_t a_addr = sbase + (uint32_t)ln * kLaneBytes + (uint32_t)op.a_slot * kSlotBytes;
                     const uint32_t b_addr = sbase + kSmemSlots + stage * kStageBytes;
                     const uint32_t idesc = ptx::umma_idesc_bf16(256, op.n, 0, 0);
@@ -375,7 +378,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                         if (i + 1 == gm.op_end) ptx::umma_commit2_mc(bar(kBarAccFull + ln), 3);
                     }
                     __syncwarp();
-                    if (a.trace && lane_id == 0) trace4(a, 0, mma_ev++, tm0, tm1, tm1, clock64());
+                    if (tracing && lane_id == 0) trace4(a, 0, mma_ev++, tm0, tm1, tm1, clock64());
                     if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -492,10 +495,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         unsigned long long ts_a = 0, ts_b = 0;
         auto signal_done = [&](int ln) {
             ptx::fence_proxy_async_smem();   // generic-proxy panel writes -> visible to the pair's MMAs / bulk stores
-            if (a.trace) ts_a = clock64();
+            if (tracing) ts_a = clock64();
             ptx::tc_fence_before();
             __syncwarp();
-            if (a.trace) ts_b = clock64();
+            if (tracing) ts_b = clock64();
             if (lane_id == 0) ptx::mbar_arrive_cluster(done_bar0 + 8u * (uint32_t)ln);
         };
         LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_gemms, kWide ? 1 : 0);
@@ -514,7 +517,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             const int next_tile = 2 * (pr + sch.stride) + (int)rank;
             const int64_t ngs = (int64_t)next_tile * NERF_TILE_M + row;
             const bool last_step = (p == a.n_gemms - 1);
-            const unsigned long long te0 = a.trace ? clock64() : 0;
+            const unsigned long long te0 = tracing ? clock64() : 0;
 
             // ---- tile prologue: before job 1 of a lane's first tile (signals), or ahead of time for the NEXT tile
             //      inside the last step of the current one (slot E is free by then; the last job carries the signal)
@@ -545,11 +548,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     for (int g = 0; g < kG; ++g) pm[g] = (G0 + g < G1) ? mask_row[(G0 + g) * NERF_TILE_M] : 0u;
                 }
             }
-            const unsigned long long te1 = a.trace ? clock64() : 0;
+            const unsigned long long te1 = tracing ? clock64() : 0;
             ptx::mbar_wait(bar(kBarAccFull + ln), (aph >> ln) & 1u);
             aph ^= 1u << ln;
             ptx::tc_fence_after();
-            const unsigned long long te2 = a.trace ? clock64() : 0;
+            const unsigned long long te2 = tracing ? clock64() : 0;
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * 256u;
             if (j.kind == EK_RELU || j.kind == EK_LINEAR || j.kind == EK_DMASK || j.kind == EK_DCOPY) {
                 if (!kBwd) {
@@ -577,17 +580,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     }
                 }
             }
-            const unsigned long long te3 = a.trace ? clock64() : 0;
+            const unsigned long long te3 = tracing ? clock64() : 0;
             if (j.enc != ENC_NONE) write_enc(j.kind, j.enc, e_addr, gs, valid);
             if (!last_step || has_next) signal_done(ln);
-            const unsigned long long te4 = a.trace ? clock64() : 0;   // the lane's next GEMM may start (accumulator drained, panels written)
+            const unsigned long long te4 = tracing ? clock64() : 0;   // the lane's next GEMM may start (accumulator drained, panels written)
 
             if (kSave) {
                 if (last_step && !has_next) ptx::fence_proxy_async_smem();   // (signal_done, which fences, was skipped)
                 __syncwarp();
                 if (lane_id == 0) ptx::mbar_arrive(bar(kBarSaveReady + ln));     // store warp: this step's panels
             }
-            if (a.trace && we == 0 && lane_id == 0) {
+            if (tracing && we == 0 && lane_id == 0) {
                 trace4(a, 1, 2 * epi_ev, te0, te1, te2, clock64());
                 trace4(a, 1, 2 * epi_ev + 1, te3, te4, ts_a, ts_b);
             }
@@ -673,6 +676,9 @@ Lane2Program *tc2_upload(const LaneProgram &p, uint32_t, std::string &err) {
         ok = ok && cudaFuncSetAttribute(k_chain2<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(k_chain2<false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(k_chain2<false, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, false, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<false, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(k_chain2<true, true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChain2Smem) == cudaSuccess;
         if (!ok) { err = std::string("tc2: cudaFuncSetAttribute failed: ") + cudaGetErrorString(cudaGetLastError()); return nullptr; }
         attr_done = true;
     }
@@ -741,7 +747,11 @@ void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st) {
         else if (l.save) launch_pdl(k_chain2<false, true, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else launch_pdl(k_chain2<false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
     } else {
-        if (l.bwd) launch_pdl(k_chain2<true, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        if (l.trace) {   // (debug timeline: narrow mode only)
+            if (l.bwd) launch_pdl(k_chain2<true, true, false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+            else if (l.save) launch_pdl(k_chain2<false, true, false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+            else launch_pdl(k_chain2<false, false, false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
+        } else if (l.bwd) launch_pdl(k_chain2<true, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else if (l.h2d_flag && l.save) launch_pdl(k_chain2<false, true, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else if (l.h2d_flag) launch_pdl(k_chain2<false, false, false, true>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
         else if (l.save) launch_pdl(k_chain2<false, true, false>, dim3(grid), dim3(kThreads), kChain2Smem, st, a);
