@@ -48,8 +48,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) {
+#ifdef NERF_B200_MBAR_DEBUG   // (a printf at every wait site costs the register-starved chain kernels measurable time)
             printf("nerf_b200: mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x,
                    threadIdx.x);
+#endif
             __trap();
         }
     }
@@ -202,8 +204,10 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     uint32_t spins = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
         if (++spins > (1u << 26)) {
+#ifdef NERF_B200_MBAR_DEBUG
             printf("nerf_b200: cluster mbarrier timeout bar=%u parity=%u block=%d thread=%d\n", bar, parity, blockIdx.x,
                    threadIdx.x);
+#endif
             __trap();
         }
     }
