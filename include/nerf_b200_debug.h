@@ -43,6 +43,11 @@ int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slo
  * batch with clock64 tracing of CTA 0. out: [3 roles (MMA issuer, epilogue warp 0, producer)][2048][2]. */
 int nerf_debug_trace(nerf_ctx *ctx, int32_t program, uint64_t *out);
 
+/* The weight-gradient work split for `cfg` over n_ctas CTAs and n_tiles 128-sample tiles (host only, no GPU needed):
+ * out[cta][10] = n_seg, then (unit, tile_begin, tile_end) x 3. unit_cost_panels[u] = half panels a ring iteration of unit u loads
+ * (capacity in *n_units on entry, unit count on exit). */
+int nerf_debug_wgrad_partition(const nerf_config *cfg, int32_t n_ctas, int64_t n_tiles, int32_t *out, int32_t *unit_cost_panels, int32_t *n_units);
+
 /* Per-CTA wall-clock marks of the last weight-gradient launch: out[cta][8] = start, first ring stage landed, all MMAs
  * done, end (ns, %globaltimer), first unit, segments, half-tile iterations, bytes loaded. Returns the CTA count (>= 0) or an error. */
 int nerf_debug_wgrad_marks(nerf_ctx *ctx, uint64_t *out, int32_t capacity_ctas);

@@ -92,6 +92,7 @@ SIGNATURES = {
     "nerf_debug_lane_plan": (ctypes.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "nerf_debug_host_pose": (ctypes.c_int, [f32, f32, vp, vp, vp]),
     "nerf_debug_read_panel": (ctypes.c_int, [vp, i32, i32, i32, vp]),
+    "nerf_debug_wgrad_partition": (ctypes.c_int, [P(NerfConfig), i32, i64, vp, vp, P(i32)]),
     "nerf_debug_wgrad_marks": (ctypes.c_int, [vp, vp, i32]),
     "nerf_debug_bench_stage": (ctypes.c_int, [vp, i32, i32, i32, i32, P(f32)]),
 }

@@ -1284,6 +1284,28 @@ int nerf_debug_plan_biases(const nerf_config *cfg, void *out, int32_t *n) {
     return NERF_OK;
 }
 
+int nerf_debug_wgrad_partition(const nerf_config *cfg, int32_t n_ctas, int64_t n_tiles, int32_t *out, int32_t *unit_cost_panels, int32_t *n_units) {
+    if (!cfg || !out || n_ctas < 1 || n_tiles < 1 || !n_units) return NERF_ERR_INVALID_ARG;
+    NetGeom g;
+    build_geom(*cfg, g);
+    TcPlan plan;
+    std::string err;
+    if (!tc_build_plan(g, plan, err)) return NERF_ERR_UNSUPPORTED;
+    std::vector<WgradWork> work;
+    tc_wgrad_partition(plan.units, n_ctas, n_tiles, work);
+    for (int c = 0; c < n_ctas; ++c) {
+        int32_t *o = out + (size_t)c * (1 + 3 * kWgMaxSeg);
+        o[0] = work[c].n_seg;
+        for (int k = 0; k < kWgMaxSeg; ++k) {
+            o[1 + 3 * k] = work[c].seg[k].unit; o[2 + 3 * k] = work[c].seg[k].tile_begin; o[3 + 3 * k] = work[c].seg[k].tile_end;
+        }
+    }
+    if (unit_cost_panels && *n_units >= (int)plan.units.size())
+        for (size_t i = 0; i < plan.units.size(); ++i) unit_cost_panels[i] = plan.units[i].n_p + plan.units[i].n_q;
+    *n_units = (int)plan.units.size();
+    return NERF_OK;
+}
+
 int nerf_debug_read_panel(nerf_ctx *c, int32_t area, int32_t tile, int32_t slot, void *out) {
     if (!c || !out) return NERF_ERR_INVALID_ARG;
     if (!c->tc) return fail(c, NERF_ERR_STATE, "debug_read_panel: not a tcgen05 context");

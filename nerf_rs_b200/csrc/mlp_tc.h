@@ -218,6 +218,7 @@ const char *tc_last_error(const TcState *s);
 int tc_debug_read(TcState *s, int area, int64_t tile, int slot, void *out, cudaStream_t st);
 // debug: run one chain program (0 fwd-train, 1 fwd-infer, 2 bwd) with clock64 tracing of CTA 0.
 // host_out: [3 roles (mma, epilogue warp 0, producer)][2048 events][2] uint64.
+void tc_wgrad_partition(const std::vector<WgradUnit> &units, int n_ctas, int64_t n_tiles, std::vector<WgradWork> &work);
 int tc_debug_wgrad_marks(TcState *s, unsigned long long *out, int capacity_ctas, cudaStream_t st);
 int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n, int S, int program, const float *rgba,
                    const float *d_sigma, const float *d_rgba, float *sigma_out, float *rgba_out, unsigned long long *host_out,

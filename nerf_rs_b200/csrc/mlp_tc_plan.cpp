@@ -429,3 +429,51 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     plan.mask_words = (np > 4) ? 16 : 8;
     return true;
 }
+
+// Split the weight-gradient units over n_ctas CTAs: each CTA gets up to kWgMaxSeg (unit, tile range) segments of (nearly) equal
+// total fitted cost. Pure host logic (tests/test_tc_plan.py checks coverage and balance).
+void tc_wgrad_partition(const std::vector<WgradUnit> &units, int n_ctas, int64_t n_tiles, std::vector<WgradWork> &work) {
+    const int G = n_ctas;
+    const int U = (int)units.size();
+    // Cost of one tile of a unit in ns, fitted to tools/wgrad_marks.py: a half-tile ring iteration takes 516 ns + 87 ns per
+    // 8 KB half panel -- a stage costs a fixed latency on top of its bytes -- (+ ~80 ns when a one-M-block unit also sums
+    // biases: its epilogue pass outlasts its four MMAs). A segment adds its ring fill + accumulator flush (~20 us).
+    std::vector<int64_t> tile_cost(U);
+    int64_t total = 0;
+    for (int i = 0; i < U; ++i) {
+        const WgradUnit &u = units[i];
+        tile_cost[i] = 2 * (87 * (u.n_p + u.n_q) + 516 + ((u.b_base >= 0 && u.n_p <= 2 && u.n_q >= 4) ? 80 : 0) + (u.sg_slot >= 0 ? 630 : 0));
+        total += tile_cost[i] * n_tiles;
+    }
+    const int64_t seg_cost = 20000;
+    // the CTAs walk the units in order, each taking `budget` worth of cost; returns whether everything was placed
+    auto place = [&](int64_t budget) -> bool {
+        work.assign((size_t)G, WgradWork{});
+        int unit = 0;
+        int64_t tile = 0;   // next unassigned tile of `unit`
+        for (int c = 0; c < G && unit < U; ++c) {
+            int64_t left = budget;
+            WgradWork &w = work[c];
+            while (unit < U && w.n_seg < kWgMaxSeg) {
+                const int64_t fit = (left - seg_cost) / tile_cost[unit];
+                if (fit < (w.n_seg ? 8 : 1)) break;     // not worth opening another segment for a few tiles
+                const int64_t take = fit < n_tiles - tile ? fit : n_tiles - tile;
+                w.seg[w.n_seg].unit = unit;
+                w.seg[w.n_seg].tile_begin = (int)tile;
+                w.seg[w.n_seg].tile_end = (int)(tile + take);
+                ++w.n_seg;
+                left -= seg_cost + take * tile_cost[unit];
+                tile += take;
+                if (tile >= n_tiles) { ++unit; tile = 0; }
+            }
+        }
+        return unit >= U;
+    };
+    int64_t lo = total / G, hi = total + seg_cost * (U + 1) + 1;   // hi: one CTA could take everything (kWgMaxSeg permitting)
+    while (!place(hi)) hi *= 2;
+    while (hi - lo > 64) {   // smallest budget that places everything
+        const int64_t mid = lo + (hi - lo) / 2;
+        if (place(mid)) hi = mid; else lo = mid;
+    }
+    place(hi);
+}

@@ -114,3 +114,36 @@ def test_unsupported_geometry_is_rejected():
         cfg = nb.default_config(hidden=hidden)
         with pytest.raises(nb.NerfError):
             U.get_plan(cfg, 0)
+
+
+@pytest.mark.parametrize("hidden,n_tiles,n_ctas", [(256, 2048, 148), (256, 42, 148), (512, 2048, 148), (128, 1, 148), (256, 2048, 16), (100, 7, 132)])
+def test_wgrad_partition_covers_every_tile_once_and_is_balanced(hidden, n_tiles, n_ctas):
+    """Host logic of the weight-gradient work split (tc_wgrad_partition): every (unit, tile) is assigned to exactly one CTA
+    segment, no CTA has more than three segments, and at bench size the fitted cost per CTA is balanced to a few percent."""
+    import ctypes
+    from nerf_rs_b200 import _lib
+    kw = dict(hidden=hidden)
+    if hidden == 100:
+        kw.update(xyz_freqs=0, dir_freqs=-1, skip_layer=0, use_rgb_head=0)
+    cfg = nb.default_config(**kw)
+    lib = _lib.load()
+    out = np.zeros((n_ctas, 10), np.int32)
+    cost = np.zeros(128, np.int32)
+    nu = ctypes.c_int32(128)
+    rc = lib.nerf_debug_wgrad_partition(ctypes.byref(cfg), n_ctas, n_tiles, out.ctypes.data_as(ctypes.c_void_p),
+                                         cost.ctypes.data_as(ctypes.c_void_p), ctypes.byref(nu))
+    assert rc == 0
+    n_units = nu.value
+    seen = np.zeros((n_units, n_tiles), np.int32)
+    load = np.zeros(n_ctas)
+    for c in range(n_ctas):
+        assert 0 <= out[c, 0] <= 3
+        for k in range(out[c, 0]):
+            u, t0, t1 = out[c, 1 + 3 * k: 4 + 3 * k]
+            assert 0 <= u < n_units and 0 <= t0 < t1 <= n_tiles
+            seen[u, t0:t1] += 1
+            load[c] += (t1 - t0) * 2 * (516 + 87 * cost[u]) + 20000
+    assert (seen == 1).all()
+    if n_tiles >= 2048 and n_ctas == 148:
+        busy = load[load > 0]
+        assert len(busy) == n_ctas and busy.max() <= 1.06 * busy.mean()
