@@ -112,7 +112,7 @@ struct nerf_ctx {
     RayRec *d_rays = nullptr;
     float *d_dirs = nullptr, *d_t = nullptr, *d_points = nullptr, *d_gold = nullptr, *d_jitter = nullptr;
     float *d_sigma = nullptr, *d_rgba = nullptr, *d_out = nullptr, *d_dsigma = nullptr, *d_drgba = nullptr;
-    float *d_ray_loss = nullptr, *d_loss = nullptr;
+    float *d_loss_partials = nullptr, *d_loss = nullptr;
     float *h_loss = nullptr;   // pinned
     int32_t *h_i32 = nullptr;  // pinned staging for index conversion
     size_t h_i32_cap = 0;
@@ -373,7 +373,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     const int nranks = c->comm.nranks;
     // compositing backward (+ pixels, + fused MSE gradient and loss) of rays [r0, r0+nr); the mean loss over ALL rays is
     // reduced by the launch that covers the last rays
-    int loss_partials_done = 0;   // per-block loss partials written so far this step (d_ray_loss holds up to 2R + 16)
+    int loss_partials_done = 0;   // per-block loss partials written so far this step (d_loss_partials holds up to 2R + 16)
     auto composite_backward = [&](int r0, int nr) -> int {
         CompositeArgs a;
         memset(&a, 0, sizeof(a));
@@ -386,8 +386,8 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         a.num_samples = c->S;
         a.gold = c->d_gold + 4 * (int64_t)r0;
         a.inv_count = 1.f / (4.f * (float)c->R);   // mean over R*4 elements (model.rs:298)
-        a.loss_partials = c->d_ray_loss + loss_partials_done;
-        a.loss_partials_first = c->d_ray_loss;
+        a.loss_partials = c->d_loss_partials + loss_partials_done;
+        a.loss_partials_first = c->d_loss_partials;
         a.loss_partials_prior = loss_partials_done;
         a.d_sigma = c->d_dsigma + s0;
         a.d_colors = c->d_drgba + 4 * s0;
@@ -575,7 +575,7 @@ int nerf_destroy(nerf_ctx *c) {
     tc_destroy(c->tc);
     void *ptrs[] = {c->d_params, c->d_grads, c->d_m, c->d_v, c->d_images, c->d_poses, c->d_render_pose, c->d_pix, c->d_view_pick,
                     c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
-                    c->d_dsigma, c->d_drgba, c->d_ray_loss, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
+                    c->d_dsigma, c->d_drgba, c->d_loss_partials, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
                     c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1], c->d_images_u8, c->d_metrics};
     for (void *p : ptrs) cudaFree(p);
     if (c->copy_stream) {
@@ -663,7 +663,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     CUB(cudaMalloc(&c->d_out, sizeof(float) * 4 * R));
     CUB(cudaMalloc(&c->d_dsigma, sizeof(float) * B));
     CUB(cudaMalloc(&c->d_drgba, sizeof(float) * 4 * B));
-    CUB(cudaMalloc(&c->d_ray_loss, sizeof(float) * (2 * (size_t)R + 16)));   // per-block loss partials: <= ceil(nr/8) per launch
+    CUB(cudaMalloc(&c->d_loss_partials, sizeof(float) * (2 * (size_t)R + 16)));   // per-block loss partials: <= ceil(nr/8) per launch
     CUB(cudaMalloc(&c->d_loss, sizeof(float) * 4));
     CUB(cudaMalloc(&c->d_render_pose, sizeof(ViewPose)));
     CUB(cudaMemsetAsync(c->d_gold, 0, sizeof(float) * 4 * R, c->stream));

@@ -48,7 +48,7 @@ struct CompositeArgs {
     float *loss_partials;      // [grid] this launch's per-block sums of squared errors (fused MSE), or NULL
     float *d_sigma;            // [R][S]
     float *d_colors;           // [R][S][4]
-    float *loss_out;           // fused mean loss (last block reduces the per-ray errors in a fixed order), or NULL
+    float *loss_out;           // fused mean loss (the last block sums the per-block partials in a fixed order), or NULL
     const float *loss_partials_first;  // first partial of the step (earlier micro-batch launches wrote theirs before this one's)
     int32_t loss_partials_prior;       // partials written by the step's earlier launches
     int32_t loss_partials_total;       // prior + this launch's grid (filled in by the launcher)

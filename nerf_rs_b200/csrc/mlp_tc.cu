@@ -14,8 +14,11 @@
 //              The positional encoding is computed in the tile prologue straight
 //              into the smem A operand of fc1 (and reused by the skip layer).
 // k_wgrad      dW^T[in x out] = sum over samples of P^T Q with both operands MN-major straight from
-//              the saved panel images; fp32 accumulators stay in TMEM across a CTA's whole sample
-//              range and are flushed once with red.global.add.f32.
+//              the saved panel images; fp32 accumulators stay in TMEM across a segment's whole tile
+//              range and are flushed with red.global.add.f32. A CTA works through up to three
+//              (unit, tile range) segments cut by tc_wgrad_partition (mlp_tc_plan.cpp) so that the
+//              fitted cost is equal across the 148 CTAs; the sigma row of fc8 is a CUDA-core GEMV
+//              inside the fc8 feature unit, fed by a d(sigma) loader warp.
 // k_pack       gathers the flat f32 [out,in] parameter blob into the bf16 chunk streams.
 #include <cstdio>
 #include <cstdlib>
