@@ -124,6 +124,19 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def synthetic_weights(cfg):
+    """`torch.manual_seed(0)`, `nn.Linear` default init per layer in order fc1..fc10, flattened the way the library
+    stores parameters (weight [out,in] row-major, then bias)."""
+    import torch
+    from nerf_rs_b200 import checkpoint
+    torch.manual_seed(0)
+    parts = []
+    for din, dout in checkpoint.layer_dims(cfg):
+        lin = torch.nn.Linear(din, dout)
+        parts += [lin.weight.detach().reshape(-1), lin.bias.detach().reshape(-1)]
+    return torch.cat(parts).numpy()
+
+
 def synthetic_images(n_views):
     rng = np.random.default_rng(1)   # SURVEY 8d: gold RGBA U[0,1) seed 1
     return rng.random((n_views, IMG * IMG, 4), dtype=np.float32)
@@ -218,8 +231,7 @@ def main():
     n_views = angles.shape[0]
     model.set_images(synthetic_images(n_views))
     model.set_view_angles(angles)
-    from oracle import model_torch as M   # weights only: torch.manual_seed(0) nn.Linear init
-    model.set_weights(M.flatten_params(M.init_params(M.ModelConfig(hidden=W), 0)).numpy())
+    model.set_weights(synthetic_weights(cfg))   # torch.manual_seed(0) nn.Linear init; no oracle code on this arm
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:

@@ -9,10 +9,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nerf_rs_b200 as nb  # noqa: E402
-from oracle import model_torch as M  # noqa: E402  (weights only)
+import bench  # noqa: E402  (synthetic weights / images, no oracle code)
 
 m = nb.NeRF(nb.default_config())
-m.set_weights(M.flatten_params(M.init_params(M.ModelConfig(hidden=256), 0)).numpy())
+m.set_weights(bench.synthetic_weights(m.cfg))
 rng = np.random.default_rng(1)
 ang = nb.get_view_angles(6)
 m.set_images(rng.random((len(ang), 800 * 800, 4), dtype=np.float32))

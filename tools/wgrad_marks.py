@@ -6,12 +6,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nerf_rs_b200 as nb
-from oracle import model_torch as M
+import bench
 
 hidden = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 cfg = nb.default_config(hidden=hidden)
 m = nb.NeRF(cfg)
-m.set_weights(M.flatten_params(M.init_params(M.ModelConfig(hidden=hidden), 0)).numpy())
+m.set_weights(bench.synthetic_weights(m.cfg))
 rng = np.random.default_rng(1)
 ang = nb.get_view_angles(6)
 m.set_images(rng.random((len(ang), 800 * 800, 4), dtype=np.float32))
