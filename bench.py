@@ -353,10 +353,10 @@ def main():
         rmodel.close()
 
     # ---- end to end through the reference-facing calls with host buffers
-    from tests import gpu_util as G
-    pts, tt, dirs, gold = G.make_points(rays, samples, 1)
-    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-    pts, tt, dirs_f, gold = pin(pts), pin(tt), pin(dirs.reshape(-1).copy()), pin(gold)
+    # host inputs of the reference call surface: one batch drawn by the library's own sampler (get_multiview_batch), read back
+    hb = model.get_batch(None, None, 64, None, True, 4242, want=("points", "t", "dirs", "gold"))
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    pts, tt, dirs_f, gold = pin(hb["points"].reshape(-1)), pin(hb["t"].reshape(-1)), pin(hb["dirs"].reshape(-1)), pin(hb["gold"].reshape(-1))
     trainer = nb.Trainer(model)
     e2e_steps = max(3, min(args.steps, 200))
     for it in range(3):
