@@ -74,3 +74,23 @@ def test_view_angle_grid_matches_oracle():
     from oracle import ray_c
     for n in (1, 2, 6):
         assert nb.get_view_angles(n).tobytes() == ray_c.get_view_angles(n).tobytes()
+
+
+def test_bench_touches_the_oracle_only_in_its_cpu_leg():
+    """bench.py may execute oracle/ only as the CPU baseline / reference arm: every `oracle` import sits inside cpu_reference()."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    offenders = []
+    for fn in ast.walk(tree):
+        if isinstance(fn, (ast.FunctionDef, ast.Module)):
+            for node in (fn.body if isinstance(fn, ast.Module) else ast.walk(fn)):
+                names = []
+                if isinstance(node, ast.ImportFrom) and node.module:
+                    names = [node.module]
+                elif isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                if any(n == "oracle" or n.startswith("oracle.") or n == "tests" or n.startswith("tests.") for n in names):
+                    where = fn.name if isinstance(fn, ast.FunctionDef) else "<module>"
+                    if where != "cpu_reference":
+                        offenders.append((where, names))
+    assert not offenders, offenders
