@@ -740,13 +740,15 @@ __global__ void k_pack_all(const PackChunk *fwd_chunks, int n_fwd, uint8_t *__re
     pdl_wait();
     const int b = blockIdx.x;
     if (b >= n_fwd + n_bwd) {
+        if (blockIdx.y != 0) return;
         const PackBias e = pb[b - n_fwd - n_bwd];
         for (int i = threadIdx.x; i < e.padded; i += blockDim.x) bias_dst[e.dst_off + i] = i < e.count ? params[e.src_base + i] : 0.f;
         return;
     }
     const PackChunk pc = b < n_fwd ? fwd_chunks[b] : bwd_chunks[b - n_fwd];
     uint8_t *dst = b < n_fwd ? fwd_dst : bwd_dst;
-    for (int i = threadIdx.x; i < pc.n_rows * 8; i += blockDim.x) {
+    // gridDim.y blocks share a chunk: the kernel is latency-bound (a few dependent-free gathers per thread), not bandwidth-bound
+    for (int i = threadIdx.x + blockDim.x * blockIdx.y; i < pc.n_rows * 8; i += blockDim.x * gridDim.y) {
         const int r = i >> 3, c8 = i & 7;
         uint32_t w[4];
 #pragma unroll
@@ -906,7 +908,7 @@ const char *tc_last_error(const TcState *s) { return s->err.c_str(); }
 
 void tc_pack_weights(TcState *s, const float *params, cudaStream_t st) {
     const int nb = (int)s->plan.biases.size();
-    launch_pdl(k_pack_all, dim3(s->fwd_train.n_chunks + s->bwd.n_chunks + nb), dim3(256), 0, st, s->fwd_train.chunks, s->fwd_train.n_chunks, s->fwd_train.wpack,
+    launch_pdl(k_pack_all, dim3(s->fwd_train.n_chunks + s->bwd.n_chunks + nb, 4), dim3(256), 0, st, s->fwd_train.chunks, s->fwd_train.n_chunks, s->fwd_train.wpack,
                                                                               s->bwd.chunks, s->bwd.n_chunks, s->bwd.wpack, s->d_pbias, nb,
                                                                               params, s->d_bias);
     ++s->bias_version;
