@@ -118,6 +118,34 @@ class NeRF {
         for (auto &p : va) { flat.push_back(p.first); flat.push_back(p.second); }
         check(ctx_, nerf_set_view_angles(ctx_, flat.data(), (int32_t)va.size()));
     }
+    // The per-batch logging projections of src/logging.rs (+ draw_predictions, display.rs:96-110), computed on the device.
+    struct BatchLog {
+        std::vector<double> screen_x, screen_y, t;                 // log_screen_coords :13-25, log_query_distances :27-39
+        std::vector<uint32_t> world_yx, world_zx, world_yz;       // log_query_points_as_maps :41-107 (100 x 100, 0x00RRGGBB)
+        std::vector<double> density_x, density_y, density_z;      // log_densities :109-134
+        std::vector<uint32_t> density_yx, density_zx, density_yz; // log_density_maps :136-195
+        std::vector<uint32_t> prediction;                          // draw_predictions: image_h x image_w back buffer
+    };
+    BatchLog log_metrics(bool densities = true, bool prediction = true) {
+        BatchLog b;
+        b.screen_x.resize(cfg_.image_w); b.screen_y.resize(cfg_.image_h); b.t.resize(2000);
+        b.world_yx.resize(10000); b.world_zx.resize(10000); b.world_yz.resize(10000);
+        nerf_metrics m{};
+        m.screen_x = b.screen_x.data(); m.screen_y = b.screen_y.data(); m.t_hist = b.t.data();
+        m.world_yx = b.world_yx.data(); m.world_zx = b.world_zx.data(); m.world_yz = b.world_yz.data();
+        if (densities) {
+            b.density_x.resize(2000); b.density_y.resize(2000); b.density_z.resize(2000);
+            b.density_yx.resize(10000); b.density_zx.resize(10000); b.density_yz.resize(10000);
+            m.density_x = b.density_x.data(); m.density_y = b.density_y.data(); m.density_z = b.density_z.data();
+            m.density_yx = b.density_yx.data(); m.density_zx = b.density_zx.data(); m.density_yz = b.density_yz.data();
+        }
+        if (prediction) {
+            b.prediction.resize((size_t)cfg_.image_w * cfg_.image_h);
+            m.prediction = b.prediction.data();
+        }
+        check(ctx_, nerf_log_metrics(ctx_, &m));
+        return b;
+    }
     nerf_ctx *ctx() { return ctx_; }
     const nerf_config &config() const { return cfg_; }
     int n_views() const { return n_views_; }

@@ -18,7 +18,8 @@ int main() {
         model.set_view_angles(angles);
         auto batch = nerf::get_multiview_batch(model, rng);
         nerf::Trainer trainer(model);
-        (void)batch; (void)trainer;
+        auto log = model.log_metrics(false, false);          // logging.rs:13-107 on the device
+        (void)batch; (void)trainer; (void)log;
     } catch (const nerf::Error &e) {
         std::printf("status %d\n", e.status);
         return e.status == NERF_ERR_NO_DEVICE ? 0 : 3;
