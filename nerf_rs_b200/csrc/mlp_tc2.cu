@@ -187,7 +187,9 @@ __device__ __forceinline__ void epi_group(const uint32_t (&r)[32], int bidx, uin
         for (int j2 = 0; j2 < 16; ++j2) {
             // packed fp32x2 add (sm_100): one instruction and one 64-bit constant operand per column pair; the bias
             // comes from the constant bank at a warp-uniform index
-            const float2 b = *reinterpret_cast<const float2 *>(&c_bias[bidx + 2 * j2]);
+            // (bias offsets are multiples of 16 floats: one 128-bit uniform constant load serves two column pairs)
+            const float4 b4 = reinterpret_cast<const float4 *>(c_bias)[(bidx >> 2) + (j2 >> 1)];
+            const float2 b = (j2 & 1) ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
             unsigned long long acc2, bias2, sum2;
             asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "r"(r[2 * j2]), "r"(r[2 * j2 + 1]));
             asm("mov.b64 %0, {%1, %2};" : "=l"(bias2) : "f"(b.x), "f"(b.y));
