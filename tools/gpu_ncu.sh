@@ -5,5 +5,5 @@ timeout 300 python tools/prof_target.py > gpurun_out/prof_target.log 2>&1 || { e
 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_short.log 2>&1 || { echo "bench failed"; exit 1; }
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_list.log 2>&1
 echo "ncu list exit $?"
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_chain2|k_wgrad|k_composite|k_sample" -s 10 -c 22 -f -o gpurun_out/prof_r01m python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1
-echo "ncu full exit $?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/prof_r01m.ncu-rep
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"k_chain2|k_wgrad|k_composite|k_sample" -s 10 -c 22 -f -o gpurun_out/prof_r01o python tools/prof_target.py > gpurun_out/ncu_full.log 2>&1
+echo "ncu full exit $?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/prof_r01o.ncu-rep
