@@ -94,3 +94,16 @@ def test_bench_touches_the_oracle_only_in_its_cpu_leg():
                     if where != "cpu_reference":
                         offenders.append((where, names))
     assert not offenders, offenders
+
+
+def test_bench_synthetic_weights_are_the_survey_init():
+    """bench.py builds its weights without oracle code; they must still be SURVEY 8d's `torch.manual_seed(0)` nn.Linear init."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import bench
+    from oracle import model_torch as M
+    for hidden in (256, 512):
+        cfg = nb.default_config(hidden=hidden)
+        want = M.flatten_params(M.init_params(M.ModelConfig(hidden=hidden), 0)).numpy()
+        assert np.array_equal(bench.synthetic_weights(cfg), want)
