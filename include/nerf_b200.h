@@ -49,7 +49,7 @@ extern "C" {
 #define NERF_MLP_SIMT 1     /* plain CUDA-core kernels with the same bf16 rounding points;
                                on-device cross-check for sizes the CPU oracle cannot reach */
 #define NERF_MLP_SIMT_FP32 2   /* the same without any bf16 rounding */
-#define NERF_MLP_TCGEN05_V1 3  /* first-generation tcgen05 chain (one tile per CTA, cta_group::1), kept for A/B runs */
+#define NERF_MLP_TCGEN05_SS 3  /* the SS-mode CTA-pair chain (activations in shared memory) at every width, kept for A/B runs */
 
 typedef struct nerf_ctx nerf_ctx;
 

@@ -37,6 +37,10 @@ int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3,
 
 /* Read one saved 16 KB panel image back: area 0 = activations, 1 = pre-activation gradients;
  * area 2 = relu bit masks (slot = mask slot, out = 128*8 uint32). */
+/* per-CTA cycle counters of the last TS-mode chain launch, [ctas][16] (library built with -DNERF_TC3_STATS; else UNSUPPORTED) */
+int nerf_debug_tc3_stats(uint64_t *out, int32_t ctas);
+/* (tag << 48 | clock) events of CTA 0's MMA thread in the last TS-mode chain launch (same debug build) */
+int nerf_debug_tc3_trace(uint64_t *out, int32_t n);
 int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slot, void *out);
 
 /* Run one chain program (0 forward-train, 1 forward-inference, 2 backward dgrad) on the resident

@@ -13,7 +13,7 @@ _lib = None
 NERF_OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_COMM, ERR_STATE, ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6
 DEPTH_REFERENCE, DEPTH_STRATIFIED = 0, 1
-MLP_TCGEN05, MLP_SIMT, MLP_SIMT_FP32, MLP_TCGEN05_V1 = 0, 1, 2, 3
+MLP_TCGEN05, MLP_SIMT, MLP_SIMT_FP32, MLP_TCGEN05_SS = 0, 1, 2, 3
 
 
 class NerfConfig(ctypes.Structure):
@@ -91,6 +91,8 @@ SIGNATURES = {
     "nerf_debug_trace": (ctypes.c_int, [vp, i32, vp]),
     "nerf_debug_lane_plan": (ctypes.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "nerf_debug_host_pose": (ctypes.c_int, [f32, f32, vp, vp, vp]),
+    "nerf_debug_tc3_stats": (ctypes.c_int, [vp, i32]),
+    "nerf_debug_tc3_trace": (ctypes.c_int, [vp, i32]),
     "nerf_debug_read_panel": (ctypes.c_int, [vp, i32, i32, i32, vp]),
     "nerf_debug_wgrad_partition": (ctypes.c_int, [P(NerfConfig), i32, i64, vp, vp, P(i32)]),
     "nerf_debug_wgrad_marks": (ctypes.c_int, [vp, vp, i32]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnerf_b200.so")
-SOURCES = ["context.cu", "sampling.cu", "composite.cu", "adam.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc_plan.cpp", "comm.cpp", "host_io.cpp", "metrics.cu"]
+SOURCES = ["context.cu", "sampling.cu", "composite.cu", "adam.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc3.cu", "mlp_tc_plan.cpp", "comm.cpp", "host_io.cpp", "metrics.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v",
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(HERE, "build", src + ".o")
         objs.append(obj)
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ["nvcc"] + NVCC_FLAGS + os.environ.get("NERF_B200_NVCC_EXTRA", "").split() + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

@@ -21,7 +21,7 @@
 
 namespace {
 
-inline bool is_tc(int impl) { return impl == NERF_MLP_TCGEN05 || impl == NERF_MLP_TCGEN05_V1; }
+inline bool is_tc(int impl) { return impl == NERF_MLP_TCGEN05 || impl == NERF_MLP_TCGEN05_SS; }
 
 struct Profiler {
     bool on = false;
@@ -482,7 +482,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
 int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick, const ViewPose *poses, int fixed_view,
                 const float *jitter, int randomize, uint64_t seed, int64_t ray_base, bool gather_gold, bool write_points) {
     // the CTA-pair MLP kernel regenerates sample positions in its prologue: points only go to HBM when somebody reads them
-    if (!(c->tc && tc_version(c->tc) == 2)) write_points = true;
+    if (!c->tc) write_points = true;
     c->points_valid = write_points;
     c->batch_poses = poses;
     SampleArgs a;
@@ -674,7 +674,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     if (is_tc(cfg->mlp_impl)) {
         std::string e;
         const int64_t max_tiles = ((int64_t)c->chunk * c->S + NERF_TILE_M - 1) / NERF_TILE_M;
-        c->tc = tc_create(c->g, max_tiles, c->num_sms, cfg->mlp_impl == NERF_MLP_TCGEN05_V1 ? 1 : 2, e);
+        c->tc = tc_create(c->g, max_tiles, c->num_sms, cfg->mlp_impl == NERF_MLP_TCGEN05_SS ? 2 : 0, e);
         if (!c->tc) return bail(NERF_ERR_UNSUPPORTED, e);
     } else {
         const int64_t bc = (int64_t)c->chunk * c->S;
@@ -882,7 +882,7 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
     // kChunks pieces on its own stream, each followed by a 4-byte counter update the kernel's prologue polls. (One launch only:
     // micro-batched batches, the v1 kernel and the SIMT cross-check take the plain copy-then-run path.)
     constexpr int kChunks = 8;
-    const bool overlap = c->tc && tc_version(c->tc) == 2 && c->chunk >= c->R && c->R >= 4 * kChunks && !getenv("NERF_B200_NO_H2D_OVERLAP");
+    const bool overlap = c->tc && c->chunk >= c->R && c->R >= 4 * kChunks && !getenv("NERF_B200_NO_H2D_OVERLAP");
     if (!overlap) {
         CU(c, cudaMemcpyAsync(c->d_points, query_points, sizeof(float) * 3 * c->B, cudaMemcpyHostToDevice, c->stream));
         CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->stream));
@@ -1304,6 +1304,18 @@ int nerf_debug_wgrad_partition(const nerf_config *cfg, int32_t n_ctas, int64_t n
         for (size_t i = 0; i < plan.units.size(); ++i) unit_cost_panels[i] = plan.units[i].n_p + plan.units[i].n_q;
     *n_units = (int)plan.units.size();
     return NERF_OK;
+}
+
+int nerf_debug_tc3_stats(uint64_t *out, int32_t ctas) {
+    if (!out || ctas < 1) return NERF_ERR_INVALID_ARG;
+    const int rc = tc3_debug_stats(reinterpret_cast<unsigned long long *>(out), ctas);
+    return rc == 0 ? NERF_OK : (rc == -1 ? NERF_ERR_UNSUPPORTED : NERF_ERR_CUDA);
+}
+
+int nerf_debug_tc3_trace(uint64_t *out, int32_t n) {
+    if (!out || n < 1) return NERF_ERR_INVALID_ARG;
+    const int rc = tc3_debug_trace(reinterpret_cast<unsigned long long *>(out), n);
+    return rc == 0 ? NERF_OK : (rc == -1 ? NERF_ERR_UNSUPPORTED : NERF_ERR_CUDA);
 }
 
 int nerf_debug_read_panel(nerf_ctx *c, int32_t area, int32_t tile, int32_t slot, void *out) {

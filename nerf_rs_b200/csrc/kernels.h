@@ -24,8 +24,6 @@ struct SampleArgs {
     float *points;             // [R][S][3] or NULL
     float *gold;               // [R][4]
 };
-void launch_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks, int n_views, int img_w, int img_h,
-                 uint64_t seed, int gen_pix, int gen_view, cudaStream_t st);
 void launch_sample(const SampleArgs &a, int num_sms, cudaStream_t st);
 void launch_encode(const float *x, float *out, int64_t n, int freqs, int repeat, cudaStream_t st);
 void launch_pack_0rgb(const float *rgba, uint32_t *out, int64_t n, cudaStream_t st);

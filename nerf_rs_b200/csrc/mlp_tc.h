@@ -121,8 +121,42 @@ struct TcProgram {
     uint32_t wpack_bytes = 0;
 };
 
+// ---- v3 (mlp_tc3.cu): TS-mode CTA-pair chain for hidden <= 256. Hidden activations never live in shared memory: the
+// epilogue writes them as bf16 into TENSOR MEMORY (tcgen05.st) and the next layer's MMAs read their A operand from there
+// (tcgen05.mma with A in TMEM). Per lane: 128 accumulator columns + 128 activation columns (256 bf16 features), so every
+// layer wider than 128 runs as two N = 128 half-GEMMs ("steps") into the same accumulator columns; the first half's
+// converted output waits in registers until the second half's MMAs have finished reading the old activations.
+#define TS_A_SMEM 0xFF         // TsOp.a_src: A operand = slot E in shared memory (SS-mode MMA)
+struct TsOp {
+    uint32_t w_off;     // byte offset of the weight chunk [n rows][64 K]; CTA rank r of the pair loads rows [r n/2, (r+1) n/2)
+    uint8_t n;          // MMA N (32, 64 or 128)
+    uint8_t a_src;      // TS_A_SMEM, or the 64-feature panel p of the lane's TMEM activations (32-bit columns 32 p ..)
+    uint8_t kcount;     // K16 steps (1, 2 or 4)
+    uint8_t first;      // first K step of the step: overwrite the accumulator
+};
+struct TsStep {
+    uint16_t op_begin, op_end;
+    uint8_t kind;           // EK_*
+    uint8_t enc;            // ENC_*: extra panel this step's epilogue writes to slot E
+    uint8_t ncols;          // accumulator columns (32 for SIGMA/RGBA, else 64 or 128)
+    uint8_t a_col;          // first 32-bit TMEM column (within the lane's activation region) of this step's bf16 output
+    uint8_t final_step;     // last step of its layer: the lane's activation columns may be rewritten after it
+    uint8_t writes_a;       // the output is a later step's A operand (0: SIGMA/RGBA, or a gradient nobody consumes)
+    uint8_t mask_word0;     // first 32-bit ReLU-mask word of this step's columns
+    uint8_t pad;
+    uint16_t bias_off;
+    int16_t save_slot, enc_save_slot, mask_slot;
+};
+struct TsProgram {
+    std::vector<TsOp> ops;
+    std::vector<TsStep> steps;     // steps[0] = tile prologue (no ops)
+    std::vector<PackChunk> chunks;
+    uint32_t wpack_bytes = 0;
+};
+
 struct TcPlan {
     TcProgram fwd_train, fwd_infer, bwd;
+    TsProgram ts_fwd_train, ts_fwd_infer, ts_bwd;   // filled when hidden <= 256
     std::vector<PackBias> biases;
     uint32_t bias_floats = 0;
     std::vector<WgradUnit> units;
@@ -187,6 +221,15 @@ struct Chain2Launch {
 void tc2_launch(const Lane2Program *P, const Chain2Launch &l, cudaStream_t st);
 int tc2_bias_upload(const void *owner, uint64_t version, const float *d_bias, int n_floats, cudaStream_t st);
 void tc2_bias_release(const void *owner);
+
+struct Ts3Program;
+Ts3Program *tc3_upload(const TsProgram &p, std::string &err);
+void tc3_free(Ts3Program *d);
+void tc3_launch(const Ts3Program *P, const Chain2Launch &l, cudaStream_t st);
+int tc3_bias_upload(const void *owner, uint64_t version, const float *d_bias, int n_floats, cudaStream_t st);
+void tc3_bias_release(const void *owner);
+int tc3_debug_stats(unsigned long long *out, int ctas);
+int tc3_debug_trace(unsigned long long *out, int n);
 
 // host-only: build all tables for a geometry. Returns false (err set) if unsupported.
 bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err);

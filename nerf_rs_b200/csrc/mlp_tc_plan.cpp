@@ -427,6 +427,146 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     }
     plan.e_slot = np > 4 ? TC_SLOT_E_WIDE : TC_SLOT_E;
     plan.mask_words = (np > 4) ? 16 : 8;
+
+    // ---- TS-mode programs (mlp_tc3.cu), hidden <= 256: every GEMM as steps of at most 128 output columns
+    if (np <= 4) {
+        struct KSrc { int a_src, kcount; int64_t src_base; int row_stride, col_stride, valid_cols; };
+        auto hidden_src = [&](std::vector<KSrc> &k, int n_panels, int64_t src_base, int row_stride, int col_stride, int col0, int valid) {
+            for (int p = 0; p < n_panels; ++p) {
+                int v = valid - 64 * p;
+                k.push_back({p, 4, src_base + (int64_t)(col0 + 64 * p) * col_stride, row_stride, col_stride, v < 0 ? 0 : (v > 64 ? 64 : v)});
+            }
+        };
+        auto emit_prologue = [&](TsProgram &P, uint8_t kind, uint8_t enc, int enc_save_slot) {
+            TsStep st;
+            memset(&st, 0, sizeof(st));
+            st.kind = kind; st.enc = enc;
+            st.save_slot = -1; st.mask_slot = -1; st.enc_save_slot = (int16_t)enc_save_slot;
+            P.steps.push_back(st);
+        };
+        // one GEMM of n_out (padded) output columns, `valid` of them real, as ceil(n_out / 128) steps
+        auto emit_gemm = [&](TsProgram &P, const std::vector<KSrc> &kin, int n_out, int valid, uint8_t kind, uint32_t bias_off, int save_slot0,
+                             int mask_slot, uint8_t enc, int enc_save_slot, bool writes_a) {
+            const bool small = kind == EK_SIGMA || kind == EK_RGBA;
+            const int nh = small ? 1 : (n_out + 127) / 128;
+            for (int h = 0; h < nh; ++h) {
+                const int ncols = small ? 32 : (n_out - 128 * h > 128 ? 128 : n_out - 128 * h);
+                const int row0 = 128 * h;
+                TsStep st;
+                memset(&st, 0, sizeof(st));
+                st.op_begin = (uint16_t)P.ops.size();
+                for (size_t i = 0; i < kin.size(); ++i) {
+                    const KSrc &k = kin[i];
+                    TsOp op;
+                    op.w_off = P.wpack_bytes;
+                    op.n = (uint8_t)ncols;
+                    op.a_src = (uint8_t)k.a_src;
+                    op.kcount = (uint8_t)k.kcount;
+                    op.first = i == 0 ? 1 : 0;
+                    P.ops.push_back(op);
+                    PackChunk pc;
+                    pc.dst_off = P.wpack_bytes;
+                    pc.n_rows = ncols;
+                    pc.src_base = k.src_base + (int64_t)row0 * k.row_stride;
+                    pc.row_stride = k.row_stride;
+                    pc.col_stride = k.col_stride;
+                    const int vr = valid - row0;
+                    pc.valid_rows = vr < 0 ? 0 : (vr > ncols ? ncols : vr);
+                    pc.valid_cols = k.valid_cols;
+                    P.chunks.push_back(pc);
+                    P.wpack_bytes += (uint32_t)ncols * 128u;
+                }
+                st.op_end = (uint16_t)P.ops.size();
+                st.kind = kind;
+                st.ncols = (uint8_t)ncols;
+                st.a_col = (uint8_t)(64 * h);
+                st.final_step = (h == nh - 1 && !small) ? 1 : 0;
+                st.writes_a = (writes_a && !small) ? 1 : 0;
+                st.mask_word0 = (uint8_t)(4 * h);
+                st.bias_off = (uint16_t)(bias_off + 128u * h);
+                st.save_slot = (int16_t)(save_slot0 < 0 ? -1 : save_slot0 + 2 * h);
+                st.mask_slot = (int16_t)mask_slot;
+                st.enc = (h == nh - 1) ? enc : (uint8_t)ENC_NONE;
+                st.enc_save_slot = (int16_t)((h == nh - 1) ? enc_save_slot : -1);
+                P.steps.push_back(st);
+            }
+        };
+        for (int train = 0; train < 2; ++train) {
+            TsProgram &P = train ? plan.ts_fwd_train : plan.ts_fwd_infer;
+            emit_prologue(P, EK_PROLOGUE_FWD, ENC_X, train ? sl.X() : -1);
+            for (int l = 1; l <= 7; ++l) {
+                const LayerGeom &L = g.L[l - 1];
+                const bool skip = g.skip_layer && l == g.skip_layer + 1;
+                std::vector<KSrc> kin;
+                if (l == 1 || skip) kin.push_back({TS_A_SMEM, 4, L.w_off, L.in_dim, 1, g.Cx});
+                if (l > 1) hidden_src(kin, np, L.w_off, L.in_dim, 1, skip ? g.Cx : 0, g.W);
+                emit_gemm(P, kin, g.Wp, g.W, EK_RELU, bias_l[l], train ? sl.H(l) : -1, train ? (l - 1) : -1, ENC_NONE, -1, true);
+            }
+            {   // fc8 sigma row, before the feature GEMM's epilogue rewrites h7. Its epilogue also writes the encoded direction
+                // into slot E for fc9 (the skip GEMM fc6, X's last reader, is long done; no first-half stash is live here)
+                const LayerGeom &L = g.L[7];
+                std::vector<KSrc> kin;
+                hidden_src(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
+                const bool dir = g.use_rgb_head && g.Cd;
+                emit_gemm(P, kin, 32, 1, EK_SIGMA, bias_s, -1, -1, dir ? ENC_D : ENC_NONE, (dir && train) ? sl.D() : -1, false);
+            }
+            if (g.use_rgb_head) {
+                {
+                    const LayerGeom &L = g.L[7];
+                    std::vector<KSrc> kin;
+                    hidden_src(kin, np, L.w_off + L.in_dim, L.in_dim, 1, 0, g.W);
+                    emit_gemm(P, kin, g.Wp, g.W, EK_LINEAR, bias_f, train ? sl.feat() : -1, -1, ENC_NONE, -1, true);
+                }
+                {
+                    const LayerGeom &L = g.L[8];
+                    std::vector<KSrc> kin;
+                    if (g.Cd) kin.push_back({TS_A_SMEM, 2, L.w_off + g.W, L.in_dim, 1, g.Cd});
+                    hidden_src(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
+                    emit_gemm(P, kin, g.W2p, g.W2, EK_RELU, bias_9, train ? sl.h9() : -1, train ? 7 : -1, ENC_NONE, -1, true);
+                }
+                {
+                    const LayerGeom &L = g.L[9];
+                    std::vector<KSrc> kin;
+                    hidden_src(kin, np2, L.w_off, L.in_dim, 1, 0, g.W2);
+                    emit_gemm(P, kin, 32, 4, EK_RGBA, bias_10, -1, -1, ENC_NONE, -1, false);
+                }
+            }
+        }
+        {
+            TsProgram &P = plan.ts_bwd;
+            if (g.use_rgb_head) {
+                emit_prologue(P, EK_PROLOGUE_BWD, ENC_NONE, sl.R());
+                {   // dH9 = dPre10 (K = 16) * W10 -> mask(h9) -> dPre9
+                    const LayerGeom &L = g.L[9];
+                    std::vector<KSrc> kin;
+                    kin.push_back({TS_A_SMEM, 1, L.w_off, 1, L.in_dim, 4});
+                    emit_gemm(P, kin, g.W2p, g.W2, EK_DMASK, 0, sl.dP9(), 7, ENC_DSIGMA, sl.Sg(), true);
+                }
+                {   // dFeat = dPre9 * W9[:, 0:W]
+                    const LayerGeom &L = g.L[8];
+                    std::vector<KSrc> kin;
+                    hidden_src(kin, np2, L.w_off, 1, L.in_dim, 0, g.W2);
+                    emit_gemm(P, kin, g.Wp, g.W, EK_DCOPY, 0, sl.dFeat(), -1, ENC_NONE, -1, true);
+                }
+            } else {
+                emit_prologue(P, EK_PROLOGUE_BWD, ENC_DSIGMA, sl.Sg());
+            }
+            {   // dH7 = [dsigma | dFeat] * W8 -> mask(h7) -> dPre7
+                const LayerGeom &L = g.L[7];
+                std::vector<KSrc> kin;
+                kin.push_back({TS_A_SMEM, 1, L.w_off, 1, L.in_dim, 1});
+                if (g.use_rgb_head) hidden_src(kin, np, L.w_off + L.in_dim, 1, L.in_dim, 0, g.W);
+                emit_gemm(P, kin, g.Wp, g.W, EK_DMASK, 0, sl.dP(7), 6, ENC_NONE, -1, true);
+            }
+            for (int l = 7; l >= 2; --l) {
+                const LayerGeom &L = g.L[l - 1];
+                const bool skip = g.skip_layer && l == g.skip_layer + 1;
+                std::vector<KSrc> kin;
+                hidden_src(kin, np, L.w_off + (skip ? g.Cx : 0), 1, L.in_dim, 0, g.W);
+                emit_gemm(P, kin, g.Wp, g.W, EK_DMASK, 0, sl.dP(l - 1), l - 2, ENC_NONE, -1, /*writes_a=*/l > 2);
+            }
+        }
+    }
     return true;
 }
 

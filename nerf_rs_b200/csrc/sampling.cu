@@ -34,22 +34,6 @@ __device__ __forceinline__ void screen_to_world(float x, float y, float width, f
     to[2] = mul(sz, inv);
 }
 
-// Philox picks for pixel rows/cols and views (replaces Tensor::randint, dataset.rs:12,19,88).
-__global__ void k_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks, int n_views, int img_w,
-                       int img_h, uint64_t seed, int gen_pix, int gen_view) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gen_pix && i < num_rays) {
-        int y = (int)(philox_uniform(seed, NERF_STREAM_PIX_Y, (uint64_t)i) * (float)img_h);
-        int x = (int)(philox_uniform(seed, NERF_STREAM_PIX_X, (uint64_t)i) * (float)img_w);
-        pix_yx[2 * i] = min(y, img_h - 1);
-        pix_yx[2 * i + 1] = min(x, img_w - 1);
-    }
-    if (gen_view && i < n_picks) {
-        int v = (int)(philox_uniform(seed, NERF_STREAM_VIEW, (uint64_t)i) * (float)n_views);
-        view_pick[i] = min(v, n_views - 1);
-    }
-}
-
 constexpr int kWarpsPerBlock = 8;
 
 // Ascending bitonic sort of 32*SPL floats held one per (register k, lane): element i = 32 k + lane. Partners closer than
@@ -98,10 +82,13 @@ k_sample(SampleArgs a) {
     const int S = a.num_samples;
     for (int r = blockIdx.x * kWarpsPerBlock + warp; r < a.num_rays; r += gridDim.x * kWarpsPerBlock) {
         // pixel / view picks: caller-supplied, or Philox in place (replaces Tensor::randint, dataset.rs:12,19,88)
+        // Every Philox stream is indexed by the GLOBAL ray (ray_index_base + r; base = rank * R in data-parallel training), so
+        // the ranks of a job draw disjoint pixels, views and jitter from one seed: N ranks x R rays = one batch of N*R rays.
+        const uint64_t gr = (uint64_t)(a.ray_index_base + r);
         int y, x;
         if (a.gen_pix) {
-            y = min((int)(philox_uniform(a.seed, NERF_STREAM_PIX_Y, (uint64_t)r) * (float)a.img_h), a.img_h - 1);
-            x = min((int)(philox_uniform(a.seed, NERF_STREAM_PIX_X, (uint64_t)r) * (float)a.img_w), a.img_w - 1);
+            y = min((int)(philox_uniform(a.seed, NERF_STREAM_PIX_Y, gr) * (float)a.img_h), a.img_h - 1);
+            x = min((int)(philox_uniform(a.seed, NERF_STREAM_PIX_X, gr) * (float)a.img_w), a.img_w - 1);
             if (lane == 0) { a.pix_out[2 * r] = y; a.pix_out[2 * r + 1] = x; }
         } else {
             y = a.pix_yx[2 * r];
@@ -110,7 +97,7 @@ k_sample(SampleArgs a) {
         int view = a.fixed_view;
         if (a.gen_view) {
             const int pick = r / a.rays_per_pick;
-            view = min((int)(philox_uniform(a.seed, NERF_STREAM_VIEW, (uint64_t)pick) * (float)a.n_views), a.n_views - 1);
+            view = min((int)(philox_uniform(a.seed, NERF_STREAM_VIEW, gr / (uint64_t)a.rays_per_pick) * (float)a.n_views), a.n_views - 1);
             if (lane == 0 && r % a.rays_per_pick == 0) a.view_out[pick] = view;
         } else if (a.view_pick) {
             view = a.view_pick[r / a.rays_per_pick];
@@ -130,7 +117,7 @@ k_sample(SampleArgs a) {
                     t = mul(__fdiv_rn((float)i, (float)S), 2.0f);  // :112,:114
                 } else {
                     const float u = a.jitter ? a.jitter[(size_t)r * S + i]
-                                             : philox_uniform(a.seed, NERF_STREAM_JITTER, (uint64_t)(a.ray_index_base + r) * S + i);
+                                             : philox_uniform(a.seed, NERF_STREAM_JITTER, gr * S + i);
                     if (a.depth_mode == 0) t = mul(u, 2.0f);                                       // :110,:114
                     else t = mul(__fdiv_rn(add((float)i, u), (float)S), 2.0f);                      // stratified
                 }
@@ -232,13 +219,6 @@ __global__ void k_full_frame_indices(int32_t *pix_yx, int y0, int y1, int img_w)
 }
 
 }  // namespace
-
-void launch_pick(int32_t *pix_yx, int32_t *view_pick, int num_rays, int n_picks, int n_views, int img_w, int img_h,
-                 uint64_t seed, int gen_pix, int gen_view, cudaStream_t st) {
-    int n = num_rays > n_picks ? num_rays : n_picks;
-    k_pick<<<(n + 255) / 256, 256, 0, st>>>(pix_yx, view_pick, num_rays, n_picks, n_views, img_w, img_h, seed, gen_pix,
-                                            gen_view);
-}
 
 template <int SPL>
 static void launch_sample_spl(const SampleArgs &a, int num_sms, cudaStream_t st) {

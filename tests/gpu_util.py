@@ -38,10 +38,11 @@ def oracle_predict(mcfg, params_t, pts, t, dirs, r, s):
 
 
 def decode_panel(u16):
-    """[8192] uint16 128B-swizzled bf16 panel image -> float32 [128, 64]."""
+    """[8192] uint16 saved panel image -> float32 [128, 64]. Saved layout (chain-kernel epilogue -> wgrad operand):
+    [half tile (64 rows)][16-byte chunk (8)][row (64)][8 bf16]."""
     r = np.arange(128)[:, None]
     c = np.arange(64)[None, :]
-    off = r * 64 + ((((c >> 3) ^ (r & 7)) & 7) << 3) + (c & 7)
+    off = (r >> 6) * 4096 + (c >> 3) * 512 + (r & 63) * 8 + (c & 7)
     v = u16[off].astype(np.uint32) << 16
     return v.view(np.float32)
 
