@@ -206,6 +206,7 @@ def main():
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--rays", type=int, default=R)
     ap.add_argument("--hidden", type=int, default=W, help="512 = BASELINE configs[4] width")
+    ap.add_argument("--mlp-impl", type=int, default=0, help="A/B only: 3 = the SS-mode chain kernel at every width (NERF_MLP_TCGEN05_SS)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -225,7 +226,7 @@ def main():
     rays, samples = args.rays, args.samples
     W = args.hidden
     FWD_FLOP, DGRAD_FLOP, WGRAD_FLOP, ACT_BYTES, GRAD_BYTES = work_constants(W)
-    cfg = nb.default_config(image_w=IMG, image_h=IMG, num_rays=rays, num_samples=samples, hidden=W)
+    cfg = nb.default_config(image_w=IMG, image_h=IMG, num_rays=rays, num_samples=samples, hidden=W, mlp_impl=args.mlp_impl)
     model = nb.NeRF(cfg, device=local)
     angles = nb.get_view_angles(N_VIEW_GRID)
     n_views = angles.shape[0]

@@ -135,11 +135,15 @@ __device__ __forceinline__ void epi_group(const float *cbias, const uint32_t (&r
     }
 }
 
-// The same for 16 columns (columns [16 kHalf, 16 kHalf + 16) of a 32-column group) -> 8 packed words: the TS-mode kernel
-// converts a group in two passes to keep 16 instead of 32 accumulator registers live next to its activation stash.
-// `signs` carries the ReLU sign bits across the two passes (kSave && EK_RELU); `mask` is the group's 32-bit ReLU mask.
-template <bool kSave, uint8_t kKind, int kHalf>
-__device__ __forceinline__ void epi_half(const float *cbias, const uint32_t (&r)[16], int bidx, uint32_t mask, uint32_t &signs, uint32_t *w) {
+// TS-mode kernel (mlp_tc3.cu): 16 accumulator columns (columns [16 kHalf, 16 kHalf + 16) of a 32-column group) -> 8 packed
+// words; a group is converted in two passes to keep 16 instead of 32 accumulator registers live.
+// ReLU masks of the TS kernels are built by the saver warps from the bf16 activations with three instructions per packed
+// word (ts_mask_word below), which fixes the bit layout: feature 2i of the group -> bit 15 - i, feature 2i + 1 -> bit 31 - i.
+__device__ __forceinline__ uint32_t ts_mask_bit(int feature) { return (feature & 1) ? (0x80000000u >> (feature >> 1)) : (0x8000u >> (feature >> 1)); }
+// accumulate the mask bits of packed word i (two non-negative bf16: nonzero <=> bit 15 of x + 0x7fff) into m
+__device__ __forceinline__ uint32_t ts_mask_word(uint32_t m, uint32_t w, int i) { return m | (((w + 0x7fff7fffu) & 0x80008000u) >> i); }
+template <uint8_t kKind, int kHalf>
+__device__ __forceinline__ void epi_half(const float *cbias, const uint32_t (&r)[16], int bidx, uint32_t mask, uint32_t *w) {
     if (kKind == EK_RELU || kKind == EK_LINEAR) {
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) {
@@ -151,18 +155,14 @@ __device__ __forceinline__ void epi_half(const float *cbias, const uint32_t (&r)
             asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum2) : "l"(acc2), "l"(bias2));
             float v0, v1;
             asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(sum2));
-            if (kSave && kKind == EK_RELU) {
-                signs = __funnelshift_l(__float_as_uint(v0), signs, 1);
-                signs = __funnelshift_l(__float_as_uint(v1), signs, 1);
-            }
             w[j2] = (kKind == EK_RELU) ? ptx::pack_bf16x2_relu(v0, v1) : ptx::pack_bf16x2(v0, v1);
         }
     } else {
         const uint32_t m = (kKind == EK_DMASK) ? mask : 0xffffffffu;
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            const float v0 = (m & (0x80000000u >> (16 * kHalf + 2 * p))) ? __uint_as_float(r[2 * p]) : 0.f;
-            const float v1 = (m & (0x80000000u >> (16 * kHalf + 2 * p + 1))) ? __uint_as_float(r[2 * p + 1]) : 0.f;
+            const float v0 = (m & ts_mask_bit(16 * kHalf + 2 * p)) ? __uint_as_float(r[2 * p]) : 0.f;
+            const float v1 = (m & ts_mask_bit(16 * kHalf + 2 * p + 1)) ? __uint_as_float(r[2 * p + 1]) : 0.f;
             w[p] = ptx::pack_bf16x2(v0, v1);
         }
     }

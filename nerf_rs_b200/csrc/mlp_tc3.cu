@@ -9,12 +9,14 @@
 //   * a layer wider than 128 runs as two N = 128 half-GEMMs ("steps") into the same accumulator columns. The first half's
 //     converted output waits in 16 registers per thread until the second half's MMAs have finished reading the old
 //     activations, then both are written in place;
-//   * shared memory holds only the encoded inputs (slot E, an SS-mode operand: K = 64 is too narrow to matter), the weight
-//     ring (8 x 8 KB half chunks per CTA) and, when training, staging buffers the epilogue fills in the weight-gradient
-//     kernel's operand layout and a store warp bulk-copies to HBM.
-// Roles per CTA (640 threads): warp 0 weight producer, warps 1 and 3 the two lanes' MMA issuers (leader; in the peer warp 1
-// relays weight arrivals), warp 2 TMEM allocator and (training) store warp, warps 4-19 epilogue (4 TMEM lane quarters x 4
-// column slices of 32).
+//   * shared memory holds only the encoded inputs (slot E, an SS-mode operand: K = 64 is too narrow to matter) and the
+//     weight ring (16 x 8 KB half chunks per CTA);
+//   * when training, four SAVER warps read each finished layer's activations back out of tensor memory and store them to
+//     HBM in the weight-gradient kernel's operand layout (and derive the ReLU masks from them) while the next layer's MMAs
+//     run: the epilogue's critical path is the same as in inference.
+// Roles per CTA (640 threads, 768 when training): warp 0 weight producer, warps 1 and 3 the two lanes' MMA issuers (leader;
+// in the peer warp 1 relays weight arrivals), warp 2 TMEM allocator, warps 4-19 epilogue (4 TMEM lane quarters x 4 column
+// slices of 32), warps 20-23 savers (training).
 // The per-tile program (TsOp / TsStep, mlp_tc_plan.cpp) travels as kernel parameters.
 #include <cstdio>
 #include <cstdlib>
@@ -32,25 +34,27 @@
 namespace {
 using namespace chain;
 
-constexpr int kStages = 8;
+constexpr int kStages = 16;
 constexpr uint32_t kStageBytes = 8192;                               // half chunk: [<= 64 rows][64 bf16]
 constexpr uint32_t kSmemRing = 2 * kSlotBytes;                       // after the two lanes' slot E
-constexpr uint32_t kStageBufBytes = 2 * kSlotBytes;                  // one step's output: <= 128 columns = 2 panel images
-constexpr uint32_t kSmemStaging = kSmemRing + kStages * kStageBytes; // [lane][2] staging buffers (training)
-constexpr uint32_t kSmemBars = kSmemStaging + 4 * kStageBufBytes;    // 224 KB
+constexpr uint32_t kSmemBars = kSmemRing + kStages * kStageBytes;    // 160 KB
 // barrier ids
-constexpr int kBarFull = 0;                   // +stage: both halves of the chunk landed (leader: own bytes + the peer's relay)
-constexpr int kBarEmpty = kStages;            // +stage: every MMA reading the stage completed (multicast commit)
+constexpr int kBarFull = 0;                   // +(step mod 16): both halves of all of a step's chunks landed (leader: own bytes + the peer's relay)
+constexpr int kBarEmpty = kStages;            // +stage: both lanes' MMAs reading the stage completed (multicast commits)
 constexpr int kBarAccFull = 2 * kStages;      // +lane
 constexpr int kBarEpiDone = 2 * kStages + 2;  // +lane (leader): both CTAs' epilogue warps finished the lane's step
-constexpr int kBarSaveReady = 2 * kStages + 4;   // +2*lane+buf: every epilogue warp has filled the staging buffer
-constexpr int kBarSaveFree = 2 * kStages + 8;    // +2*lane+buf: the bulk store has finished reading it
-constexpr int kNumBars = 2 * kStages + 12;
+constexpr int kBarActReady = 2 * kStages + 4; // +lane (training): this CTA's epilogue warps have written a layer's activations
+constexpr int kBarActSaved = 2 * kStages + 6; // +lane (training): the saver warps have read them out of tensor memory
+constexpr int kBarToken = 2 * kStages + 8;    // +lane (leader): the lane's issuer may issue its next step (see the issuers)
+constexpr int kNumBars = 2 * kStages + 10;
 constexpr uint32_t kChain3Smem = kSmemBars + kNumBars * 8 + 16;
+static_assert(kStages == 16, "the FULL barriers are indexed by step counter mod 16");
 static_assert(kChain3Smem <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
 constexpr int kEpiWarps = 16;
 constexpr int kServiceWarps = 4;
-constexpr int kThreads = 32 * (kServiceWarps + kEpiWarps);   // 640 threads, 96 registers per thread at launch
+constexpr int kSaverWarps = 4;                // training only: one per TMEM lane quarter
+constexpr int kThreadsInfer = 32 * (kServiceWarps + kEpiWarps);                  // 640 threads, 96 registers per thread at launch
+constexpr int kThreadsTrain = 32 * (kServiceWarps + kEpiWarps + kSaverWarps);    // 768 threads, 80 registers per thread at launch
 constexpr int kMaxOps = 80, kMaxSteps = 24;
 constexpr uint32_t kLaneCols = 256, kActCol = 128;   // TMEM columns per lane; activations start at column 128 of the lane
 
@@ -165,7 +169,7 @@ __device__ __noinline__ void write_enc(const Chain3Args &a, uint32_t row, int h,
         }
 
 template <bool kBwd, bool kSave, bool kH2D>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain3(const __grid_constant__ Chain3Args a) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrain : kThreadsInfer, 1) k_chain3(const __grid_constant__ Chain3Args a) {
     pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = ptx::smem_u32(smem);
@@ -188,9 +192,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             ptx::mbar_init(bar(kBarAccFull + l), 1);
             ptx::mbar_init(bar(kBarEpiDone + l), 2 * kEpiWarps);
         }
-        for (int i = 0; i < 4; ++i) {
-            ptx::mbar_init(bar(kBarSaveReady + i), kEpiWarps);
-            ptx::mbar_init(bar(kBarSaveFree + i), 1);
+        for (int l = 0; l < 2; ++l) {
+            ptx::mbar_init(bar(kBarActReady + l), kEpiWarps);
+            ptx::mbar_init(bar(kBarActSaved + l), kSaverWarps);
+            ptx::mbar_init(bar(kBarToken + l), 1);
         }
         ptx::fence_mbar_init();
     }
@@ -202,34 +207,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
     const uint32_t tmem_base = *tmem_ptr_smem;
     pdl_wait();
 
-    // Register rebalancing (setmaxnreg): 128 x 64 + 512 x 104 registers = the CTA's launch allocation of 640 x 96
+    // Register rebalancing (setmaxnreg). Inference: 128 x 64 + 512 x 104 = the CTA's launch allocation of 640 x 96 registers;
+    // training (4 more warps): 128 x 40 (service) + 128 x 56 (savers) + 512 x 96 (epilogue) = 768 x 80.
     if (warp < kServiceWarps) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (kSave) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == 0 || (warp == 1 && rank != 0)) {
             // ===== warp 0 (both CTAs): weight producer -- this CTA's half of every chunk, once per lane group
             // ===== warp 1 of the peer: relays "my half landed" to the leader's full barrier, in the same order
             const bool producer = warp == 0;
+            // One FULL barrier per STEP (slot = step counter mod 16, as many slots as ring stages: a slot cannot come round again
+            // before its step's stages have been released, i.e. before both issuers have seen it): the producer arms it with the
+            // step's total bytes, every chunk of the step completes on it, and an issuer waits once per step instead of once
+            // per chunk (~140 cycles each, even when the chunk landed long ago).
             LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, phase = 0, gstep = 0;
             int g, nl, pr0, pr1;
             while (sch.next(g, nl, pr0, pr1)) {
                 const TsStep st = a.steps[g + 1];
-                for (int i = st.op_begin; i < st.op_end; ++i) {
-                    if (producer) {
-                        const uint32_t half = (uint32_t)a.ops[i].n * 64u;   // (n / 2) rows * 128 B
+                const uint32_t full = bar(kBarFull + (int)(gstep & 15u));
+                if (producer) {
+                    uint32_t total = 0;
+                    for (int i = st.op_begin; i < st.op_end; ++i) total += (uint32_t)a.ops[i].n * 64u;   // (n / 2) rows * 128 B each
+                    for (int i = st.op_begin; i < st.op_end; ++i) {
+                        const uint32_t half = (uint32_t)a.ops[i].n * 64u;
                         const uint8_t *src = a.wpack + a.ops[i].w_off + rank * half;
                         ptx::mbar_wait(bar(kBarEmpty + stage), phase ^ 1u);
                         if (ptx::elect_one()) {
-                            ptx::mbar_arrive_expect_tx(bar(kBarFull + stage), half);
-                            ptx::bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src, half, bar(kBarFull + stage));
+                            if (i == st.op_begin) ptx::mbar_arrive_expect_tx(full, total);
+                            ptx::bulk_g2s(sbase + kSmemRing + stage * kStageBytes, src, half, full);
                         }
-                    } else {
-                        ptx::mbar_wait(bar(kBarFull + stage), phase);
-                        if (lane_id == 0) ptx::mbar_arrive_cluster(ptx::mapa(bar(kBarFull + stage), 0));
+                        __syncwarp();
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
+                } else {
+                    ptx::mbar_wait(full, (gstep >> 4) & 1u);
+                    if (lane_id == 0) ptx::mbar_arrive_cluster(ptx::mapa(full, 0));
                     __syncwarp();
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
+                ++gstep;
             }
         } else if (warp == 1 || (warp == 3 && rank == 0)) {
             // ================= leader: one MMA issuer PER LANE (warp 1: lane 0, warp 3: lane 1) =================
@@ -238,10 +254,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             // of tensor work (tools/tc3_stats.py --trace). With one issuer per lane those latencies overlap with the other lane's
             // MMAs: each issuer has two step times per step. Both wait for the same weight stages; a stage is released when both
             // lanes' MMAs on it have completed (EMPTY counts two commits; a lone lane commits twice).
+            // The two issuers must ALTERNATE: left alone they issue at the same time, their MMAs interleave in the tensor pipe's
+            // queue, both lanes' steps finish together and the pipe idles through both epilogues (measured: 62 % busy). A token
+            // (TOKEN[lane]) orders the issue bursts -- lane 0's step g, lane 1's step g, lane 0's step g + 1, ... -- and is handed
+            // on as soon as a burst is ISSUED, ~600 cycles of queued MMAs before it completes.
             const int ln = warp == 1 ? 0 : 1;
             LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
-            uint32_t stage = 0, phase = 0;
+            uint32_t stage = 0, gstep = 0;
             uint32_t done_phase = 0;
+            uint32_t tok_phase = 0;     // parity to wait for on TOKEN[ln]
+            bool tok_pending = false;   // lane 0: lane 1 will hand the token back (it issued in the previous group)
             int g, nl, pr0, pr1;
             TC3_STAT_DECL(s_epi); TC3_STAT_DECL(s_full); TC3_STAT_DECL(s_steps); TC3_STAT_DECL(s_issue);
 #ifdef NERF_TC3_STATS
@@ -257,13 +279,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
 #pragma unroll
                     for (int i = 0; i < 5; ++i) if (i < n_ops) ops[i] = a.ops[ob + i];
                     if (ln == 0) TC3_TRACE(tr_n, 1);
-                    {   // the weights first: these waits overlap with the lane's epilogue, which is what the issuer really waits for
+                    {   // the weights first: this wait overlaps with the lane's epilogue, which is what the issuer really waits for
                         const unsigned long long t0 = TC3_CLK(); (void)t0;
-                        uint32_t sg = stage, ph = phase;
-                        for (int i = 0; i < n_ops; ++i) {
-                            ptx::mbar_wait(bar(kBarFull + sg), ph);
-                            if (++sg == kStages) { sg = 0; ph ^= 1u; }
-                        }
+                        ptx::mbar_wait(bar(kBarFull + (int)(gstep & 15u)), (gstep >> 4) & 1u);
                         TC3_STAT_ADD(s_full, t0);
                     }
                     if (ln == 0) TC3_TRACE(tr_n, 3);
@@ -271,6 +289,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     ptx::mbar_wait(bar(kBarEpiDone + ln), done_phase);
                     TC3_STAT_ADD(s_epi, t0); }
                     done_phase ^= 1u;
+                    if (ln == 1 || tok_pending) {   // my turn? (lane 0 owns the token at the start and whenever lane 1 has no tile)
+                        ptx::mbar_wait(bar(kBarToken + ln), tok_phase);
+                        tok_phase ^= 1u;
+                    }
                     ptx::tc_fence_after();
                     if (ln == 0) TC3_TRACE(tr_n, 2);
                     const unsigned long long ti0 = TC3_CLK(); (void)ti0;
@@ -305,8 +327,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                             }
                         }
                         ptx::umma_commit2_mc(bar(kBarAccFull + ln), 3);
+                        if (nl == 2) ptx::mbar_arrive(bar(kBarToken + (ln ^ 1)));   // the other lane's turn
                         if (ln == 0) TC3_TRACE(tr_n, 5);
                     }
+                    tok_pending = nl == 2;
 #ifdef NERF_TC3_STATS
                     tr_n = __shfl_sync(0xffffffffu, tr_n, __ffs(__activemask()) - 1);
                     ++s_steps;
@@ -315,40 +339,70 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     TC3_STAT_ADD(s_issue, ti0);
                 }
                 stage += (uint32_t)n_ops;
-                if (stage >= (uint32_t)kStages) { stage -= kStages; phase ^= 1u; }
+                if (stage >= (uint32_t)kStages) stage -= kStages;
+                ++gstep;
             }
 #ifdef NERF_TC3_STATS
             if (ln == 0) { TC3_STAT_PUT(0, clock64() - s_t0); TC3_STAT_PUT(1, s_epi); TC3_STAT_PUT(2, s_full); TC3_STAT_PUT(3, s_steps); TC3_STAT_PUT(4, s_issue); }
 #endif
-        } else if (kSave && warp == 2) {
-            // ================= store warp (training; the TMEM allocator warp): one bulk copy per saved step, staging buffer -> the tile's save area
-            LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
-            uint32_t rph = 0;    // bit (2 lane + buf): parity to wait for on SAVE_READY
-            uint32_t bufs = 0;   // bit lane: staging buffer of the lane's next saved step
-            int p, nl, pr0, pr1;
-            while (sch.next(p, nl, pr0, pr1)) {
-                const TsStep st = a.steps[p + 1];
-                if (st.save_slot < 0) continue;
-                for (int ln = 0; ln < nl; ++ln) {
-                    const int pr = ln ? pr1 : pr0;
-                    const int idx = 2 * ln + (int)((bufs >> ln) & 1u);
-                    bufs ^= 1u << ln;
-                    ptx::mbar_wait(bar(kBarSaveReady + idx), (rph >> idx) & 1u);
-                    rph ^= 1u << idx;
-                    if (lane_id == 0) {
-                        uint8_t *dst = a.save_base + ((size_t)(2 * pr + (int)rank) * a.save_slots + (size_t)st.save_slot) * kSlotBytes;
-                        ptx::bulk_s2g(dst, sbase + kSmemStaging + (uint32_t)idx * kStageBufBytes, (uint32_t)(st.ncols >> 6) * kSlotBytes);
-                        ptx::bulk_commit();
-                        ptx::bulk_wait_read<0>();
-                        ptx::mbar_arrive(bar(kBarSaveFree + idx));
+        }
+    } else if (kSave && warp >= kServiceWarps + kEpiWarps) {
+        // ================= saver warps (training): activations TMEM -> HBM, off the epilogue's critical path =================
+        // Warp q reads its lane quarter of a finished layer's bf16 activations back from tensor memory (the MMAs of the next
+        // layer read them at the same time), stores them in the weight-gradient kernel's operand layout (chunk-major: the
+        // warp's 32 rows are 512 contiguous bytes per 16-byte chunk) and, for the forward ReLU layers, derives the ReLU masks
+        // from them (mask bit = bf16 activation != 0, three instructions per packed word). The epilogue only waits (ACT_SAVED) before it overwrites the columns,
+        // a layer later.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const uint32_t q = (uint32_t)(warp & 3);
+        const uint32_t row = q * 32u + (uint32_t)lane_id;
+        LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
+        uint32_t rph = 0;   // bit lane: parity to wait for on ACT_READY
+        int p, nl, pr0, pr1;
+        while (sch.next(p, nl, pr0, pr1)) {
+            const TsStep st = a.steps[p + 1];
+            if (!st.final_step || st.save_slot < 0) continue;
+            const int n_groups = ((int)st.a_col + ((int)st.ncols >> 1)) >> 4;   // 16 TMEM columns = 32 features = half a panel
+            const int slot0 = (int)st.save_slot - ((int)st.a_col >> 5);         // the layer's first saved panel
+            for (int ln = 0; ln < nl; ++ln) {
+                const int tile = 2 * (ln ? pr1 : pr0) + (int)rank;
+                ptx::mbar_wait(bar(kBarActReady + ln), (rph >> ln) & 1u);
+                rph ^= 1u << ln;
+                ptx::tc_fence_after();
+                const uint32_t act = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * kLaneCols + kActCol;
+                uint8_t *gbase = a.save_base + ((size_t)tile * a.save_slots + (size_t)slot0) * kSlotBytes + cm_row_off(row);
+                uint32_t *mbase = (!kBwd && st.mask_slot >= 0) ? a.mask_base + ((size_t)tile * a.mask_slots + st.mask_slot) * NERF_TILE_M * 8 + row : nullptr;
+                for (int g2 = 0; g2 < n_groups; g2 += 2) {
+                    uint32_t w0[16], w1[16];
+                    ptx::tmem_ld16(act + 16u * (uint32_t)g2, w0);
+                    if (g2 + 1 < n_groups) ptx::tmem_ld16(act + 16u * (uint32_t)(g2 + 1), w1);
+                    ptx::tmem_ld_wait();
+                    uint8_t *gp = gbase + (size_t)(g2 >> 1) * kSlotBytes;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) st_global_v4(gp + (uint32_t)c * kCmChunkStride, w0[4 * c], w0[4 * c + 1], w0[4 * c + 2], w0[4 * c + 3]);
+                    if (g2 + 1 < n_groups) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) st_global_v4(gp + (uint32_t)(4 + c) * kCmChunkStride, w1[4 * c], w1[4 * c + 1], w1[4 * c + 2], w1[4 * c + 3]);
                     }
-                    __syncwarp();
+                    if (mbase) {
+                        uint32_t m0 = 0, m1 = 0;   // (bit layout: chain_common.cuh, ts_mask_word)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            m0 = ts_mask_word(m0, w0[i], i);
+                            m1 = ts_mask_word(m1, w1[i], i);
+                        }
+                        mbase[(size_t)g2 * NERF_TILE_M] = m0;
+                        if (g2 + 1 < n_groups) mbase[(size_t)(g2 + 1) * NERF_TILE_M] = m1;
+                    }
                 }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane_id == 0) ptx::mbar_arrive(bar(kBarActSaved + ln));
             }
-            if (lane_id == 0) ptx::bulk_wait_all<0>();
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        if (kSave) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ================= epilogue warps =================
         // warp (q, h): TMEM lane quarter q (rows 32q..32q+31), 32-column group h of the step's accumulator
         const uint32_t we = (uint32_t)(warp - kServiceWarps);
@@ -356,10 +410,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         const int h = (int)(we >> 2);
         const uint32_t row = q * 32u + (uint32_t)lane_id;
         uint32_t aph = 0;     // bit l: parity to wait for on ACC_FULL[l]
-        uint32_t sph = 0;     // bit (2 lane + buf): SAVE_FREE phase bookkeeping (training)
-        uint32_t bufs = 0;    // bit lane: staging buffer of the lane's next saved step
+        uint32_t sph = 0;     // bit lane: ACT_SAVED phase bookkeeping (training)
         const uint32_t done_bar0 = ptx::mapa(bar(kBarEpiDone), 0);   // leader's EPI_DONE[0] in the cluster window
-        TC3_STAT_DECL(s_acc); TC3_STAT_DECL(s_ld); TC3_STAT_DECL(s_free); TC3_STAT_DECL(s_items); TC3_STAT_DECL(s_sig); TC3_STAT_DECL(s_stage);
+        TC3_STAT_DECL(s_acc); TC3_STAT_DECL(s_ld); TC3_STAT_DECL(s_free); TC3_STAT_DECL(s_items); TC3_STAT_DECL(s_sig); TC3_STAT_DECL(s_conv); TC3_STAT_DECL(s_st); TC3_STAT_DECL(s_h1); TC3_STAT_DECL(s_h2); TC3_STAT_DECL(s_pl); TC3_STAT_DECL(s_pro);
         const unsigned long long s_e0 = TC3_CLK(); (void)s_e0;
         // wrote_e: this warp has written slot E since its last signal (generic-proxy writes -> visible to the pair's MMAs)
         auto signal_done = [&](int ln, bool wrote_e = false) {
@@ -374,53 +427,54 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
 
         // 32 accumulator columns of this warp's quarter -> 16 packed bf16 pairs, in two passes of 16 columns (16 accumulator
         // registers live). `sig`: release the accumulator to the lane's next MMAs as soon as it is in registers.
-        auto convert = [&](uint8_t kind, uint32_t tcol, int bidx, uint32_t &m, uint32_t (&w)[16], bool sig, int ln) {
-            uint32_t signs = 0;
-            uint32_t r[16];
-            const unsigned long long tl0 = TC3_CLK(); (void)tl0;
-            ptx::tmem_ld16(tcol, r);
-            ptx::tmem_ld_wait();
-            TC3_STAT_ADD(s_ld, tl0);
-            if (!kBwd) {
-                if (kind == EK_RELU) epi_half<kSave, EK_RELU, 0>(c_bias3, r, bidx, m, signs, w);
-                else epi_half<kSave, EK_LINEAR, 0>(c_bias3, r, bidx, m, signs, w);
+        auto convert = [&](uint8_t kind, uint32_t tcol, int bidx, uint32_t m, uint32_t (&w)[16], bool sig, int ln) {
+            const unsigned long long tc0 = TC3_CLK(); (void)tc0;
+            auto half0 = [&](const uint32_t (&r)[16]) {
+                if (!kBwd) { if (kind == EK_RELU) epi_half<EK_RELU, 0>(c_bias3, r, bidx, m, w); else epi_half<EK_LINEAR, 0>(c_bias3, r, bidx, m, w); }
+                else { if (kind == EK_DMASK) epi_half<EK_DMASK, 0>(c_bias3, r, bidx, m, w); else epi_half<EK_DCOPY, 0>(c_bias3, r, bidx, m, w); }
+            };
+            auto half1 = [&](const uint32_t (&r)[16]) {
+                if (!kBwd) { if (kind == EK_RELU) epi_half<EK_RELU, 1>(c_bias3, r, bidx, m, w + 8); else epi_half<EK_LINEAR, 1>(c_bias3, r, bidx, m, w + 8); }
+                else { if (kind == EK_DMASK) epi_half<EK_DMASK, 1>(c_bias3, r, bidx, m, w + 8); else epi_half<EK_DCOPY, 1>(c_bias3, r, bidx, m, w + 8); }
+            };
+            if constexpr (!kSave) {
+                // inference (104 registers): both 16-column loads in flight at once, the accumulator is released before any arithmetic
+                uint32_t r0[16], r1[16];
+                ptx::tmem_ld16(tcol, r0);
+                ptx::tmem_ld16(tcol + 16u, r1);
+                ptx::tmem_ld_wait();
+                TC3_STAT_ADD(s_ld, tc0);
+                if (sig) signal_done(ln);
+                half0(r0);
+                half1(r1);
             } else {
-                if (kind == EK_DMASK) epi_half<kSave, EK_DMASK, 0>(c_bias3, r, bidx, m, signs, w);
-                else epi_half<kSave, EK_DCOPY, 0>(c_bias3, r, bidx, m, signs, w);
+                // training (96 registers): two passes of 16 columns
+                uint32_t r[16];
+                ptx::tmem_ld16(tcol, r);
+                ptx::tmem_ld_wait();
+                TC3_STAT_ADD(s_ld, tc0);
+                half0(r);
+                ptx::tmem_ld16(tcol + 16u, r);
+                ptx::tmem_ld_wait();
+                if (sig) signal_done(ln);
+                half1(r);
             }
-            ptx::tmem_ld16(tcol + 16u, r);
-            ptx::tmem_ld_wait();
-            if (sig) signal_done(ln);
-            if (!kBwd) {
-                if (kind == EK_RELU) epi_half<kSave, EK_RELU, 1>(c_bias3, r, bidx, m, signs, w + 8);
-                else epi_half<kSave, EK_LINEAR, 1>(c_bias3, r, bidx, m, signs, w + 8);
-            } else {
-                if (kind == EK_DMASK) epi_half<kSave, EK_DMASK, 1>(c_bias3, r, bidx, m, signs, w + 8);
-                else epi_half<kSave, EK_DCOPY, 1>(c_bias3, r, bidx, m, signs, w + 8);
-            }
-            if (!kBwd) m = ~signs;   // bit (31 - col) set = pre-activation sign bit clear
+            TC3_STAT_ADD(s_conv, tc0);
         };
-        // training: the warp's 16 words of a step's output in the weight-gradient kernel's operand layout -> staging buffer
-        // (double-buffered per lane) -> bulk store by the store warp
-        auto stage_save = [&](const TsStep &st, int ln, bool active, const uint32_t (&w)[16]) {
-            if (!kSave || st.save_slot < 0) return;
-            const uint32_t idx = 2u * (uint32_t)ln + ((bufs >> ln) & 1u);
-            bufs ^= 1u << ln;
-            { const unsigned long long t0 = TC3_CLK(); (void)t0;
-            ptx::mbar_wait(bar(kBarSaveFree + (int)idx), ((sph >> idx) & 1u) ^ 1u);
-            TC3_STAT_ADD(s_free, t0); }
-            sph ^= 1u << idx;
-            const unsigned long long ts0 = TC3_CLK(); (void)ts0;
-            if (active) {
-                const uint32_t dst = sbase + kSmemStaging + idx * kStageBufBytes + (uint32_t)(h >> 1) * kSlotBytes + cm_row_off(row) +
-                                     (uint32_t)(h & 1) * 4u * kCmChunkStride;
-#pragma unroll
-                for (int c = 0; c < 4; ++c) st_shared_v4(dst + (uint32_t)c * kCmChunkStride, w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-            }
-            ptx::fence_proxy_async_smem();
+        // training: the saver warps must have read the lane's previous activations out of tensor memory before they are
+        // overwritten (normally long done: a layer's MMAs take ~4 000 cycles), and are told when the new ones are in place
+        auto wait_act_saved = [&](int ln) {
+            if (!kSave) return;
+            const unsigned long long t0 = TC3_CLK(); (void)t0;
+            ptx::mbar_wait(bar(kBarActSaved + ln), ((sph >> ln) & 1u) ^ 1u);
+            TC3_STAT_ADD(s_free, t0);
+            sph ^= 1u << ln;
+        };
+        auto act_ready = [&](int ln) {   // (after tcgen05.wait::st)
+            if (!kSave) return;
+            ptx::tc_fence_before();
             __syncwarp();
-            if (lane_id == 0) ptx::mbar_arrive(bar(kBarSaveReady + (int)idx));
-            TC3_STAT_ADD(s_stage, ts0);
+            if (lane_id == 0) ptx::mbar_arrive(bar(kBarActReady + ln));
         };
         auto mask_addr = [&](const TsStep &st, int tile) -> uint32_t * {
             return a.mask_base + ((size_t)tile * a.mask_slots + st.mask_slot) * NERF_TILE_M * 8 + (size_t)(st.mask_word0 + h) * NERF_TILE_M + row;
@@ -450,42 +504,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
         // ---- one half of a two-step layer (N = 128 columns each, every warp active). kSecond = false: convert, release the
         // accumulator, keep the 16 words in `stash`; kSecond = true: convert, then write both halves over the old activations
         // (all of the layer's MMAs have completed once the second half's accumulator is full) and hand them to the next layer.
-        auto half_step = [&](auto second, int ln, int p, int pr, int stride, uint32_t (&stash)[16]) {
+        auto half_step = [&](auto second, int ln, int p, int pr, int stride, uint32_t (&stash)[16], uint32_t m) {
             constexpr bool kSecond = decltype(second)::value;
             const TsStep st = a.steps[p + 1];
-            const int tile = 2 * pr + (int)rank;
-            uint32_t m = 0;
-            uint32_t *mp = nullptr;
-            if (st.mask_slot >= 0) {
-                mp = mask_addr(st, tile);
-                if (kBwd && st.kind == EK_DMASK) m = *mp;   // issued now, consumed after the accumulator wait
-            }
             wait_acc(ln);
             const uint32_t tlane = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * kLaneCols;
             const int bidx = bias_base + (int)st.bias_off + 32 * h;
             if (!kSecond) {
                 convert(st.kind, tlane + 32u * (uint32_t)h, bidx, m, stash, true, ln);
-                if (kSave && !kBwd && mp) *mp = m;
-                stage_save(st, ln, true, stash);
             } else {
                 // the accumulator is full = every MMA of the layer has read the old activations: the first half goes in place
                 // right away (its registers are free before the second half's accumulator columns are loaded)
                 const uint32_t act = tlane + kActCol + 16u * (uint32_t)h;
-                if (st.writes_a) ptx::tmem_st16(act, stash);
+                if (st.save_slot >= 0) wait_act_saved(ln);   // (the savers have had the layer's whole MMA time: normally long done)
+                ptx::tmem_st16(act, stash);
                 uint32_t w[16];
                 convert(st.kind, tlane + 32u * (uint32_t)h, bidx, m, w, false, ln);
-                if (st.writes_a) {
-                    ptx::tmem_st16(act + (uint32_t)st.a_col, w);
-                    ptx::tmem_st_wait();
-                }
+                { const unsigned long long t0 = TC3_CLK(); (void)t0;
+                ptx::tmem_st16(act + (uint32_t)st.a_col, w);
+                ptx::tmem_st_wait();
+                TC3_STAT_ADD(s_st, t0); }
                 if (p != a.n_steps - 1) {
                     signal_done(ln);
                 } else if (pr + stride < a.n_pairs) {   // the tile's last step: it also carries the lane's next tile prologue
                     write_prologue(ln, pr + stride);
                     signal_done(ln, true);
                 }
-                if (kSave && !kBwd && mp) *mp = m;
-                stage_save(st, ln, true, w);
+                if (st.save_slot >= 0) act_ready(ln);
             }
         };
 
@@ -510,15 +555,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             // activations (final step of a layer) or a new slot-E panel
             const bool need_signal = !last_step || has_next;   // (nobody waits after the cluster's very last step)
             const bool early = need_signal && !st.final_step && st.enc == ENC_NONE && !pre_next;
-            uint32_t *mp = nullptr;
             uint32_t m = 0;
-            if (st.mask_slot >= 0 && active && !small) {
-                mp = mask_addr(st, tile);
-                if (kBwd && st.kind == EK_DMASK) m = *mp;
+            if (kBwd && st.kind == EK_DMASK && active) m = *mask_addr(st, tile);
+            if (!kBwd && p == a.n_steps - 2 && has_next) {
+                // the next tile's encoding is written inside the tile's last step: pull its inputs towards the SM a step early
+                const int64_t ngs = (int64_t)(2 * (pr + stride) + (int)rank) * NERF_TILE_M + row;
+                if (ngs < a.n_samples) {
+                    if (a.points) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.points + 3 * ngs));
+                    else {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.t + ngs));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rays + ngs / a.S));
+                    }
+                }
             }
             wait_acc(ln);
             const uint32_t tlane = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * kLaneCols;
-            uint32_t w[16];
             if (small) {
                 uint32_t r[16];
                 if (h == 0) {
@@ -540,12 +591,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                     }
                 }
             } else {
+                // a single-step layer: its MMAs are done, the new activations go in place
+                if (st.save_slot >= 0) wait_act_saved(ln);
                 if (active) {
+                    uint32_t w[16];
                     convert(st.kind, tlane + 32u * (uint32_t)h, bias_base + (int)st.bias_off + 32 * h, m, w, early, ln);
-                    if (st.writes_a) {   // a single-step layer: its MMAs are done, the new activations go in place
-                        ptx::tmem_st16(tlane + kActCol + (uint32_t)st.a_col + 16u * (uint32_t)h, w);
-                        ptx::tmem_st_wait();
-                    }
+                    ptx::tmem_st16(tlane + kActCol + (uint32_t)st.a_col + 16u * (uint32_t)h, w);
+                    ptx::tmem_st_wait();
                 } else if (early) {
                     signal_done(ln);
                 }
@@ -553,10 +605,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             if (st.enc != ENC_NONE) write_enc<kH2D>(a, row, h, st.kind, st.enc, e_addr, gs, valid, save_at(tile, st.enc_save_slot));
             if (pre_next) write_prologue(ln, pr + stride);
             if (!early && need_signal) signal_done(ln, st.enc != ENC_NONE || pre_next);
-            if (!small) {
-                if (kSave && !kBwd && mp) *mp = m;
-                stage_save(st, ln, active, w);
-            }
+            if (!small && st.save_slot >= 0) act_ready(ln);
         };
 
         LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
@@ -574,19 +623,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
             if (st.ncols == 128 && !st.final_step && st.kind != EK_SIGMA && st.kind != EK_RGBA) {
                 // a two-step layer: both lanes' first halves, then both lanes' second halves; the first halves' words stay in
                 // registers that are live only inside this block
+                if (kBwd && p + 3 < a.n_steps) {
+                    // the next layer's mask lines are prefetched towards the SM a layer ahead (the first item of a layer still
+                    // loads its word on the spot: then an L2 hit instead of a DRAM access)
+                    const TsStep n0 = a.steps[p + 3], n1 = a.steps[p + 4];
+                    if (n0.kind == EK_DMASK && n0.mask_slot >= 0) {
+                        auto pf = [&](const TsStep &ns, int pr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(mask_addr(ns, 2 * pr + (int)rank))); };
+                        pf(n0, pr0);
+                        pf(n1, pr0);
+                        if (nl == 2) { pf(n0, pr1); pf(n1, pr1); }
+                    }
+                }
                 uint32_t s0[16], s1[16];
-                half_step(std::false_type{}, 0, p, pr0, sch.stride, s0);
-                if (nl == 2) half_step(std::false_type{}, 1, p, pr1, sch.stride, s1);
+                // backward: every item's ReLU-mask word is loaded one item ahead (an item is too short to hide the load behind
+                // its own accumulator wait; loading further ahead keeps more words live than the register budget has)
+                const bool masked = kBwd && st.kind == EK_DMASK;
+                const int t0i = 2 * pr0 + (int)rank, t1i = 2 * pr1 + (int)rank;
+                const TsStep stb = a.steps[p + 2];   // the layer's second step
+                uint32_t ma = 0, mb = 0;
+                if (masked) {
+                    ma = *mask_addr(st, t0i);
+                    if (nl == 2) mb = *mask_addr(st, t1i);
+                }
+                { const unsigned long long t0 = TC3_CLK(); (void)t0;
+                half_step(std::false_type{}, 0, p, pr0, sch.stride, s0, ma);
+                if (masked) ma = *mask_addr(stb, t0i);
+                if (nl == 2) {
+                    half_step(std::false_type{}, 1, p, pr1, sch.stride, s1, mb);
+                    if (masked) mb = *mask_addr(stb, t1i);
+                }
+                TC3_STAT_ADD(s_h1, t0); }
                 sch.next(p, nl, pr0, pr1);   // the layer's second step: same tiles, same lanes
-                half_step(std::true_type{}, 0, p, pr0, sch.stride, s0);
-                if (nl == 2) half_step(std::true_type{}, 1, p, pr1, sch.stride, s1);
+                { const unsigned long long t0 = TC3_CLK(); (void)t0;
+                half_step(std::true_type{}, 0, p, pr0, sch.stride, s0, ma);
+                if (nl == 2) half_step(std::true_type{}, 1, p, pr1, sch.stride, s1, mb);
+                TC3_STAT_ADD(s_h2, t0); }
             } else {
+                const unsigned long long t0 = TC3_CLK(); (void)t0;
                 plain_step(0, p, pr0, sch.stride);
                 if (nl == 2) plain_step(1, p, pr1, sch.stride);
+                TC3_STAT_ADD(s_pl, t0);
             }
         }
 #ifdef NERF_TC3_STATS
-        if (we == 0) { TC3_STAT_PUT(8, clock64() - s_e0); TC3_STAT_PUT(9, s_acc); TC3_STAT_PUT(10, s_ld); TC3_STAT_PUT(11, s_free); TC3_STAT_PUT(12, s_items); TC3_STAT_PUT(13, s_sig); TC3_STAT_PUT(14, s_stage); }
+        if (we == 0 && lane_id == 0) { g_tc3_stats[blockIdx.x * 16 + 5] = s_h1; g_tc3_stats[blockIdx.x * 16 + 6] = s_h2; g_tc3_stats[blockIdx.x * 16 + 7] = s_pl; }
+#endif
+#ifdef NERF_TC3_STATS
+        if (we == 0) { TC3_STAT_PUT(8, clock64() - s_e0); TC3_STAT_PUT(9, s_acc); TC3_STAT_PUT(10, s_ld); TC3_STAT_PUT(11, s_free); TC3_STAT_PUT(12, s_items); TC3_STAT_PUT(13, s_sig); TC3_STAT_PUT(14, s_conv); TC3_STAT_PUT(15, s_st); }
 #endif
     }
 
@@ -621,6 +704,8 @@ Ts3Program *tc3_upload(const TsProgram &p, std::string &err) {
     }
     Ts3Program *d = new Ts3Program();
     d->prog = p;
+    if (getenv("NERF_TC3_NOMASK"))   // timing experiment only (wrong gradients): the backward chain without its ReLU-mask loads
+        for (auto &st : d->prog.steps) if (st.kind == EK_DMASK) st.kind = EK_DCOPY;
     return d;
 }
 void tc3_free(Ts3Program *d) { delete d; }
@@ -694,9 +779,9 @@ void tc3_launch(const Ts3Program *P, const Chain2Launch &l, cudaStream_t st) {
     const int max_clusters = l.num_sms / 2;
     const int clusters = a.n_pairs < max_clusters ? a.n_pairs : max_clusters;
     const int grid = 2 * clusters;
-    if (l.bwd) launch_pdl(k_chain3<true, true, false>, dim3(grid), dim3(kThreads), kChain3Smem, st, a);
-    else if (l.h2d_flag && l.save) launch_pdl(k_chain3<false, true, true>, dim3(grid), dim3(kThreads), kChain3Smem, st, a);
-    else if (l.h2d_flag) launch_pdl(k_chain3<false, false, true>, dim3(grid), dim3(kThreads), kChain3Smem, st, a);
-    else if (l.save) launch_pdl(k_chain3<false, true, false>, dim3(grid), dim3(kThreads), kChain3Smem, st, a);
-    else launch_pdl(k_chain3<false, false, false>, dim3(grid), dim3(kThreads), kChain3Smem, st, a);
+    if (l.bwd) launch_pdl(k_chain3<true, true, false>, dim3(grid), dim3(kThreadsTrain), kChain3Smem, st, a);
+    else if (l.h2d_flag && l.save) launch_pdl(k_chain3<false, true, true>, dim3(grid), dim3(kThreadsTrain), kChain3Smem, st, a);
+    else if (l.h2d_flag) launch_pdl(k_chain3<false, false, true>, dim3(grid), dim3(kThreadsInfer), kChain3Smem, st, a);
+    else if (l.save) launch_pdl(k_chain3<false, true, false>, dim3(grid), dim3(kThreadsTrain), kChain3Smem, st, a);
+    else launch_pdl(k_chain3<false, false, false>, dim3(grid), dim3(kThreadsInfer), kChain3Smem, st, a);
 }

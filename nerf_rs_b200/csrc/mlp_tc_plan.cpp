@@ -563,7 +563,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 const bool skip = g.skip_layer && l == g.skip_layer + 1;
                 std::vector<KSrc> kin;
                 hidden_src(kin, np, L.w_off + (skip ? g.Cx : 0), 1, L.in_dim, 0, g.W);
-                emit_gemm(P, kin, g.Wp, g.W, EK_DMASK, 0, sl.dP(l - 1), l - 2, ENC_NONE, -1, /*writes_a=*/l > 2);
+                emit_gemm(P, kin, g.Wp, g.W, EK_DMASK, 0, sl.dP(l - 1), l - 2, ENC_NONE, -1, true);   // (dPre1 has no consumer, but the saver warps read it from there)
             }
         }
     }

@@ -7,4 +7,4 @@ echo "pytest mlp exit $rc"; tail -n 25 gpurun_out/pytest_step.log
 timeout 600 python -m pytest tests/test_gpu_e2e.py tests/test_metrics.py -q -m gpu -x --timeout 120 > gpurun_out/pytest_step2.log 2>&1; rc=$?
 echo "pytest e2e exit $rc"; tail -n 15 gpurun_out/pytest_step2.log
 [ $rc -ne 0 ] && exit 1
-bash tools/gpu_ab_lib.sh 2>&1 | tee gpurun_out/ab.log
+bash tools/gpu_ab_impl.sh 2>&1 | tee gpurun_out/ab.log

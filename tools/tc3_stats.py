@@ -23,8 +23,9 @@ def show(tag, st):
     print(f"{tag}: MMA thread total {med(lead[:, 0]):.0f} clk, wait EPI_DONE {med(lead[:, 1]):.0f} ({med(lead[:, 1]) / max(steps, 1):.0f}/step), "
           f"wait weights {med(lead[:, 2]):.0f}, MMA issue blocks {med(lead[:, 4]):.0f} ({med(lead[:, 4]) / max(steps, 1):.0f}/step), lane steps {steps:.0f}")
     print(f"{tag}: epilogue total {med(st[:, 8]):.0f} clk, wait ACC_FULL {med(st[:, 9]):.0f} ({med(st[:, 9]) / max(items, 1):.0f}/item), "
-          f"ld {med(st[:, 10]):.0f} ({med(st[:, 10]) / max(items, 1):.0f}/item), wait SAVE_FREE {med(st[:, 11]) / max(items, 1):.0f}/item, "
-          f"signal {med(st[:, 13]) / max(items, 1):.0f}/item, staging {med(st[:, 14]) / max(items, 1):.0f}/item, items {items:.0f}")
+          f"ld {med(st[:, 10]):.0f} ({med(st[:, 10]) / max(items, 1):.0f}/item), wait ACT_SAVED {med(st[:, 11]) / max(items, 1):.0f}/item, "
+          f"signal {med(st[:, 13]) / max(items, 1):.0f}/item, convert (incl. ld, early signal) {med(st[:, 14]) / max(items, 1):.0f}/item, "
+          f"tcgen05.st+wait {med(st[:, 15]) / max(items, 1):.0f}/item, items {items:.0f}")
 
 
 def show_trace(model, first=0, count=120):
@@ -47,6 +48,11 @@ def show_trace(model, first=0, count=120):
         print("  ".join(line))
 
 
+def show2(tag, st):
+    med = lambda a: float(np.median(a))
+    print(f"{tag}: epilogue warp 0 time in first halves {med(st[:, 5]):.0f}, second halves {med(st[:, 6]):.0f}, plain steps {med(st[:, 7]):.0f} (of {med(st[:, 8]):.0f})")
+
+
 def main():
     rays, samples = 4096, 64
     cfg = nb.default_config(image_w=800, image_h=800, num_rays=rays, num_samples=samples, hidden=256)
@@ -58,16 +64,18 @@ def main():
     for _ in range(3):
         m.predict(train=False)
     m.sync()
-    show("infer ", read_stats(m))
+    show("infer ", read_stats(m)); show2("infer ", read_stats(m))
     if "--trace" in sys.argv:
         show_trace(m, 200, 160)
     for i in range(3):
         m.train_iter(i)
     m.sync()
-    show("dgrad ", read_stats(m))   # the last k_chain3 launch of a training iteration is the backward chain
+    show("dgrad ", read_stats(m)); show2("dgrad ", read_stats(m))
+    if "--trace" in sys.argv:
+        show_trace(m, 200, 200)   # the last k_chain3 launch of a training iteration is the backward chain
     m.predict(train=True)
     m.sync()
-    show("fwd-tr", read_stats(m))
+    show("fwd-tr", read_stats(m)); show2("fwd-tr", read_stats(m))
 
 
 if __name__ == "__main__":
