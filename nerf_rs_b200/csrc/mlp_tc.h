@@ -126,7 +126,13 @@ struct TcProgram {
 // (tcgen05.mma with A in TMEM). Per lane: 128 accumulator columns + 128 activation columns (256 bf16 features), so every
 // layer wider than 128 runs as two N = 128 half-GEMMs ("steps") into the same accumulator columns; the first half's
 // converted output waits in registers until the second half's MMAs have finished reading the old activations.
-#define TS_A_SMEM 0xFF         // TsOp.a_src: A operand = slot E in shared memory (SS-mode MMA)
+#define TS_A_SMEM 0xFF         // TsOp.a_src: A operand = the lane's slot E_A in shared memory (SS-mode MMA): encoded positions / dPre10
+#define TS_A_SMEM_B 0xFE       //             the lane's slot E_B: encoded direction / d(sigma)
+// TsStep.pre_enc: after its own signal, the step's epilogue writes a slot-E panel of the lane's NEXT tile -- off every critical
+// path, as soon as the current tile's last reader of that slot has completed (the first tile's panels are written up front)
+#define TS_PRE_NONE 0
+#define TS_PRE_A 1
+#define TS_PRE_B 2
 struct TsOp {
     uint32_t w_off;     // byte offset of the weight chunk [n rows][64 K]; CTA rank r of the pair loads rows [r n/2, (r+1) n/2)
     uint8_t n;          // MMA N (32, 64 or 128)
@@ -137,15 +143,18 @@ struct TsOp {
 struct TsStep {
     uint16_t op_begin, op_end;
     uint8_t kind;           // EK_*
-    uint8_t enc;            // ENC_*: extra panel this step's epilogue writes to slot E
+    uint8_t enc;            // (prologue entry) ENC_* of panel A
     uint8_t ncols;          // accumulator columns (32 for SIGMA/RGBA, else 64 or 128)
     uint8_t a_col;          // first 32-bit TMEM column (within the lane's activation region) of this step's bf16 output
     uint8_t final_step;     // last step of its layer: the lane's activation columns may be rewritten after it
     uint8_t writes_a;       // the output is a later step's A operand (0: SIGMA/RGBA, or a gradient nobody consumes)
     uint8_t mask_word0;     // first 32-bit ReLU-mask word of this step's columns
-    uint8_t pad;
+    uint8_t pre_enc;        // TS_PRE_*
     uint16_t bias_off;
     int16_t save_slot, enc_save_slot, mask_slot;
+    // prologue entry (steps[0]) only: kind/enc/enc_save_slot describe panel A; b_enc/b_save_slot panel B (ENC_NONE = no panel B)
+    uint8_t b_enc, pad;
+    int16_t b_save_slot;
 };
 struct TsProgram {
     std::vector<TsOp> ops;

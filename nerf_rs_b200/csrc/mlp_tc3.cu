@@ -9,8 +9,10 @@
 //   * a layer wider than 128 runs as two N = 128 half-GEMMs ("steps") into the same accumulator columns. The first half's
 //     converted output waits in 16 registers per thread until the second half's MMAs have finished reading the old
 //     activations, then both are written in place;
-//   * shared memory holds only the encoded inputs (slot E, an SS-mode operand: K = 64 is too narrow to matter) and the
-//     weight ring (16 x 8 KB half chunks per CTA);
+//   * shared memory holds only the encoded inputs (two slot-E panels per lane, SS-mode operands: K <= 64 is too narrow to
+//     matter) and the weight ring (16 x 8 KB half chunks per CTA). A tile's slot-E panels are written during the PREVIOUS
+//     tile, as soon as their last reader there has completed, after the writing step's own signal: the positional encoding
+//     (32 sin/cos per thread, exposed global loads) is off every critical path;
 //   * when training, four SAVER warps read each finished layer's activations back out of tensor memory and store them to
 //     HBM in the weight-gradient kernel's operand layout (and derive the ReLU masks from them) while the next layer's MMAs
 //     run: the epilogue's critical path is the same as in inference.
@@ -36,8 +38,8 @@ using namespace chain;
 
 constexpr int kStages = 16;
 constexpr uint32_t kStageBytes = 8192;                               // half chunk: [<= 64 rows][64 bf16]
-constexpr uint32_t kSmemRing = 2 * kSlotBytes;                       // after the two lanes' slot E
-constexpr uint32_t kSmemBars = kSmemRing + kStages * kStageBytes;    // 160 KB
+constexpr uint32_t kSmemRing = 4 * kSlotBytes;                       // after the two lanes' slots E_A, E_B
+constexpr uint32_t kSmemBars = kSmemRing + kStages * kStageBytes;    // 192 KB
 // barrier ids
 constexpr int kBarFull = 0;                   // +(step mod 16): both halves of all of a step's chunks landed (leader: own bytes + the peer's relay)
 constexpr int kBarEmpty = kStages;            // +stage: both lanes' MMAs reading the stage completed (multicast commits)
@@ -45,8 +47,7 @@ constexpr int kBarAccFull = 2 * kStages;      // +lane
 constexpr int kBarEpiDone = 2 * kStages + 2;  // +lane (leader): both CTAs' epilogue warps finished the lane's step
 constexpr int kBarActReady = 2 * kStages + 4; // +lane (training): this CTA's epilogue warps have written a layer's activations
 constexpr int kBarActSaved = 2 * kStages + 6; // +lane (training): the saver warps have read them out of tensor memory
-constexpr int kBarToken = 2 * kStages + 8;    // +lane (leader): the lane's issuer may issue its next step (see the issuers)
-constexpr int kNumBars = 2 * kStages + 10;
+constexpr int kNumBars = 2 * kStages + 8;
 constexpr uint32_t kChain3Smem = kSmemBars + kNumBars * 8 + 16;
 static_assert(kStages == 16, "the FULL barriers are indexed by step counter mod 16");
 static_assert(kChain3Smem <= 232448, "exceeds the 227 KB per-CTA shared memory limit");
@@ -195,8 +196,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
         for (int l = 0; l < 2; ++l) {
             ptx::mbar_init(bar(kBarActReady + l), kEpiWarps);
             ptx::mbar_init(bar(kBarActSaved + l), kSaverWarps);
-            ptx::mbar_init(bar(kBarToken + l), 1);
         }
+        *reinterpret_cast<volatile uint32_t *>(smem + kSmemBars + kNumBars * 8 + 8) = 0u;   // the issuers' lock
         ptx::fence_mbar_init();
     }
     if (warp == 2) ptx::tmem_alloc2<512>(ptx::smem_u32(const_cast<uint32_t *>(tmem_ptr_smem)));
@@ -254,16 +255,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
             // of tensor work (tools/tc3_stats.py --trace). With one issuer per lane those latencies overlap with the other lane's
             // MMAs: each issuer has two step times per step. Both wait for the same weight stages; a stage is released when both
             // lanes' MMAs on it have completed (EMPTY counts two commits; a lone lane commits twice).
-            // The two issuers must ALTERNATE: left alone they issue at the same time, their MMAs interleave in the tensor pipe's
-            // queue, both lanes' steps finish together and the pipe idles through both epilogues (measured: 62 % busy). A token
-            // (TOKEN[lane]) orders the issue bursts -- lane 0's step g, lane 1's step g, lane 0's step g + 1, ... -- and is handed
-            // on as soon as a burst is ISSUED, ~600 cycles of queued MMAs before it completes.
+            // The two issuers must not issue AT THE SAME TIME: their MMAs would interleave in the tensor pipe's queue, both lanes'
+            // steps would finish together and the pipe would idle through both epilogues. A lock in shared memory makes an issue
+            // burst exclusive; it is released as soon as the burst is ISSUED (~600 cycles of queued MMAs before it completes), so
+            // the other lane's burst queues up right behind it. (A strict hand-over token was tried first: it also makes a lane
+            // whose epilogue is late hold up the lane that is ready.)
             const int ln = warp == 1 ? 0 : 1;
             LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
             uint32_t stage = 0, gstep = 0;
             uint32_t done_phase = 0;
-            uint32_t tok_phase = 0;     // parity to wait for on TOKEN[ln]
-            bool tok_pending = false;   // lane 0: lane 1 will hand the token back (it issued in the previous group)
+            const uint32_t lock = bars + 8u * (uint32_t)kNumBars + 8u;   // (4 bytes after the TMEM base pointer word pair)
             int g, nl, pr0, pr1;
             TC3_STAT_DECL(s_epi); TC3_STAT_DECL(s_full); TC3_STAT_DECL(s_steps); TC3_STAT_DECL(s_issue);
 #ifdef NERF_TC3_STATS
@@ -271,7 +272,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
 #endif
             const unsigned long long s_t0 = TC3_CLK();
             const uint32_t d_tmem = tmem_base + (uint32_t)ln * kLaneCols;
-            const uint64_t ad0 = ptx::umma_desc_sw128(sbase + (uint32_t)ln * kSlotBytes, 16, 1024);   // the lane's slot E
+            const uint64_t adA = ptx::umma_desc_sw128(sbase + (uint32_t)(2 * ln) * kSlotBytes, 16, 1024);       // the lane's slot E_A
+            const uint64_t adB = ptx::umma_desc_sw128(sbase + (uint32_t)(2 * ln + 1) * kSlotBytes, 16, 1024);   // and E_B
             while (sch.next(g, nl, pr0, pr1)) {
                 const int ob = a.steps[g + 1].op_begin, n_ops = a.steps[g + 1].op_end - ob;
                 if (ln < nl) {
@@ -289,14 +291,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
                     ptx::mbar_wait(bar(kBarEpiDone + ln), done_phase);
                     TC3_STAT_ADD(s_epi, t0); }
                     done_phase ^= 1u;
-                    if (ln == 1 || tok_pending) {   // my turn? (lane 0 owns the token at the start and whenever lane 1 has no tile)
-                        ptx::mbar_wait(bar(kBarToken + ln), tok_phase);
-                        tok_phase ^= 1u;
-                    }
                     ptx::tc_fence_after();
                     if (ln == 0) TC3_TRACE(tr_n, 2);
                     const unsigned long long ti0 = TC3_CLK(); (void)ti0;
                     if (ptx::elect_one()) {
+                        if (nl == 2) {   // the pipe is mine for this burst
+                            uint32_t old;
+                            do {
+                                asm volatile("atom.shared.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "r"(lock) : "memory");
+                            } while (old != 0u);
+                        }
                         uint32_t sg = stage;
 #pragma unroll
                         for (int i = 0; i < 5; ++i) {
@@ -305,7 +309,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
                                 const uint64_t bd0 = ptx::umma_desc_sw128(sbase + kSmemRing + sg * kStageBytes, 16, 1024);
                                 const uint32_t idesc = ptx::umma_idesc_bf16(256, op.n, 0, 0);
                                 const uint32_t acc0 = op.first ? 0u : 1u;
-                                if (op.a_src == TS_A_SMEM) {
+                                if (op.a_src >= TS_A_SMEM_B) {
+                                    const uint64_t ad0 = op.a_src == TS_A_SMEM ? adA : adB;
                                     ptx::umma_ss2(d_tmem, ad0, bd0, idesc, acc0);
                                     if (op.kcount > 1) ptx::umma_ss2(d_tmem, ad0 + 2u, bd0 + 2u, idesc, 1u);
                                     if (op.kcount > 2) {
@@ -327,10 +332,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
                             }
                         }
                         ptx::umma_commit2_mc(bar(kBarAccFull + ln), 3);
-                        if (nl == 2) ptx::mbar_arrive(bar(kBarToken + (ln ^ 1)));   // the other lane's turn
+                        if (nl == 2) asm volatile("st.shared.u32 [%0], %1;" ::"r"(lock), "r"(0u) : "memory");
                         if (ln == 0) TC3_TRACE(tr_n, 5);
                     }
-                    tok_pending = nl == 2;
 #ifdef NERF_TC3_STATS
                     tr_n = __shfl_sync(0xffffffffu, tr_n, __ffs(__activemask()) - 1);
                     ++s_steps;
@@ -414,10 +418,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
         const uint32_t done_bar0 = ptx::mapa(bar(kBarEpiDone), 0);   // leader's EPI_DONE[0] in the cluster window
         TC3_STAT_DECL(s_acc); TC3_STAT_DECL(s_ld); TC3_STAT_DECL(s_free); TC3_STAT_DECL(s_items); TC3_STAT_DECL(s_sig); TC3_STAT_DECL(s_conv); TC3_STAT_DECL(s_st); TC3_STAT_DECL(s_h1); TC3_STAT_DECL(s_h2); TC3_STAT_DECL(s_pl); TC3_STAT_DECL(s_pro);
         const unsigned long long s_e0 = TC3_CLK(); (void)s_e0;
-        // wrote_e: this warp has written slot E since its last signal (generic-proxy writes -> visible to the pair's MMAs)
-        auto signal_done = [&](int ln, bool wrote_e = false) {
+        uint32_t e_dirty = 0;   // bit lane: this warp has written a slot-E panel of the lane since its last signal
+        auto signal_done = [&](int ln) {
             const unsigned long long t0 = TC3_CLK(); (void)t0;
-            if (wrote_e) ptx::fence_proxy_async_smem();
+            if (e_dirty & (1u << ln)) {   // generic-proxy writes -> visible to the pair's MMAs
+                ptx::fence_proxy_async_smem();
+                e_dirty &= ~(1u << ln);
+            }
             ptx::tc_fence_before();          // (tcgen05.ld / tcgen05.st of this warp have been waited for)
             __syncwarp();
             if (lane_id == 0) ptx::mbar_arrive_cluster(done_bar0 + 8u * (uint32_t)ln);
@@ -490,15 +497,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
             ptx::tc_fence_after();
         };
 
-        // the tile prologue of pair tile `pr` for lane `ln`: encoded inputs (forward) / fc10 pre-activation gradients (backward)
-        // into the lane's slot E -- before the first step of the lane's first tile, or inside the last step of the previous one
-        auto write_prologue = [&](int ln, int pr) {
+        // A slot-E panel of pair tile `pr` for lane `ln`: panel A = encoded positions (forward) / fc10 pre-activation gradients
+        // (backward), panel B = encoded direction / d(sigma). The lanes' first tiles get theirs before step 0; later tiles'
+        // panels are written by the steps the program marks (TsStep.pre_enc), after those steps' own signals.
+        auto write_panel = [&](int ln, int pr, bool panel_b) {
             const TsStep pj = a.steps[0];
             const int tile = 2 * pr + (int)rank;
             const int64_t gs = (int64_t)tile * NERF_TILE_M + row;
-            uint8_t *gsave = (kSave && pj.enc_save_slot >= 0)
-                                 ? a.save_base + ((size_t)tile * a.save_slots + (size_t)pj.enc_save_slot) * kSlotBytes + cm_row_off(row) : nullptr;
-            write_enc<kH2D>(a, row, h, pj.kind, pj.enc, sbase + (uint32_t)ln * kSlotBytes, gs, gs < a.n_samples, gsave);
+            const int slot = panel_b ? (int)pj.b_save_slot : (int)pj.enc_save_slot;
+            uint8_t *gsave = (kSave && slot >= 0) ? a.save_base + ((size_t)tile * a.save_slots + (size_t)slot) * kSlotBytes + cm_row_off(row) : nullptr;
+            write_enc<kH2D>(a, row, h, panel_b ? (uint8_t)EK_RELU : pj.kind, panel_b ? pj.b_enc : pj.enc,
+                            sbase + (uint32_t)(2 * ln + (panel_b ? 1 : 0)) * kSlotBytes, gs, gs < a.n_samples, gsave);
+            e_dirty |= 1u << ln;
+        };
+        auto pre_encode = [&](const TsStep &st, int ln, int pr, int stride) {
+            if (st.pre_enc != TS_PRE_NONE && pr + stride < a.n_pairs) write_panel(ln, pr + stride, st.pre_enc == TS_PRE_B);
         };
 
         // ---- one half of a two-step layer (N = 128 columns each, every warp active). kSecond = false: convert, release the
@@ -512,6 +525,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
             const int bidx = bias_base + (int)st.bias_off + 32 * h;
             if (!kSecond) {
                 convert(st.kind, tlane + 32u * (uint32_t)h, bidx, m, stash, true, ln);
+                pre_encode(st, ln, pr, stride);
             } else {
                 // the accumulator is full = every MMA of the layer has read the old activations: the first half goes in place
                 // right away (its registers are free before the second half's accumulator columns are loaded)
@@ -524,13 +538,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
                 ptx::tmem_st16(act + (uint32_t)st.a_col, w);
                 ptx::tmem_st_wait();
                 TC3_STAT_ADD(s_st, t0); }
-                if (p != a.n_steps - 1) {
-                    signal_done(ln);
-                } else if (pr + stride < a.n_pairs) {   // the tile's last step: it also carries the lane's next tile prologue
-                    write_prologue(ln, pr + stride);
-                    signal_done(ln, true);
-                }
+                if (p != a.n_steps - 1 || pr + stride < a.n_pairs) signal_done(ln);   // (nobody waits after the cluster's very last step)
                 if (st.save_slot >= 0) act_ready(ln);
+                pre_encode(st, ln, pr, stride);
             }
         };
 
@@ -538,36 +548,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
         // prologue (of the lane's first tile, or of its next tile inside the current tile's last step)
         auto plain_step = [&](int ln, int p, int pr, int stride) {
             const bool has_next = pr + stride < a.n_pairs;
-            const uint32_t e_addr = sbase + (uint32_t)ln * kSlotBytes;
             const int tile = 2 * pr + (int)rank;
             const int64_t gs = (int64_t)tile * NERF_TILE_M + row;
             const bool valid = gs < a.n_samples;
             const bool last_step = (p == a.n_steps - 1);
-            // training: the row's position in the chunk-major saved image of panel `slot` of tile `tl`
-            auto save_at = [&](int tl, int slot) -> uint8_t * {
-                return (kSave && slot >= 0) ? a.save_base + ((size_t)tl * a.save_slots + (size_t)slot) * kSlotBytes + cm_row_off(row) : nullptr;
-            };
-            const bool pre_next = last_step && has_next;
             const TsStep st = a.steps[p + 1];
             const bool active = 32 * h < (int)st.ncols;
             const bool small = st.kind == EK_SIGMA || st.kind == EK_RGBA;
             // the lane's MMAs may go on as soon as the accumulator is in registers, unless this step also hands over new
-            // activations (final step of a layer) or a new slot-E panel
+            // activations (final step of a layer)
             const bool need_signal = !last_step || has_next;   // (nobody waits after the cluster's very last step)
-            const bool early = need_signal && !st.final_step && st.enc == ENC_NONE && !pre_next;
+            const bool early = need_signal && !st.final_step;
             uint32_t m = 0;
             if (kBwd && st.kind == EK_DMASK && active) m = *mask_addr(st, tile);
-            if (!kBwd && p == a.n_steps - 2 && has_next) {
-                // the next tile's encoding is written inside the tile's last step: pull its inputs towards the SM a step early
-                const int64_t ngs = (int64_t)(2 * (pr + stride) + (int)rank) * NERF_TILE_M + row;
-                if (ngs < a.n_samples) {
-                    if (a.points) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.points + 3 * ngs));
-                    else {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.t + ngs));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.rays + ngs / a.S));
-                    }
-                }
-            }
             wait_acc(ln);
             const uint32_t tlane = tmem_base + ((q * 32u) << 16) + (uint32_t)ln * kLaneCols;
             if (small) {
@@ -602,21 +595,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kSave ? kThreadsTrai
                     signal_done(ln);
                 }
             }
-            if (st.enc != ENC_NONE) write_enc<kH2D>(a, row, h, st.kind, st.enc, e_addr, gs, valid, save_at(tile, st.enc_save_slot));
-            if (pre_next) write_prologue(ln, pr + stride);
-            if (!early && need_signal) signal_done(ln, st.enc != ENC_NONE || pre_next);
+            if (!early && need_signal) signal_done(ln);
             if (!small && st.save_slot >= 0) act_ready(ln);
+            pre_encode(st, ln, pr, stride);
         };
 
         LaneSched sch(cluster, n_clusters, a.n_pairs, a.n_steps, 0);
         int p, nl, pr0, pr1;
         while (sch.next(p, nl, pr0, pr1)) {
             if (p == 0 && pr0 < sch.stride) {   // the lanes' first tiles: their prologues are steps of their own
-                write_prologue(0, pr0);
-                signal_done(0, true);
+                const bool has_b = a.steps[0].b_enc != ENC_NONE;
+                write_panel(0, pr0, false);
+                if (has_b) write_panel(0, pr0, true);
+                signal_done(0);
                 if (nl == 2) {
-                    write_prologue(1, pr1);
-                    signal_done(1, true);
+                    write_panel(1, pr1, false);
+                    if (has_b) write_panel(1, pr1, true);
+                    signal_done(1);
                 }
             }
             const TsStep st = a.steps[p + 1];

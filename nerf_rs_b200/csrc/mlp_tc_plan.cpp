@@ -437,14 +437,17 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 k.push_back({p, 4, src_base + (int64_t)(col0 + 64 * p) * col_stride, row_stride, col_stride, v < 0 ? 0 : (v > 64 ? 64 : v)});
             }
         };
-        auto emit_prologue = [&](TsProgram &P, uint8_t kind, uint8_t enc, int enc_save_slot) {
+        auto emit_prologue = [&](TsProgram &P, uint8_t kind, uint8_t enc, int enc_save_slot, uint8_t b_enc, int b_save_slot) {
             TsStep st;
             memset(&st, 0, sizeof(st));
             st.kind = kind; st.enc = enc;
             st.save_slot = -1; st.mask_slot = -1; st.enc_save_slot = (int16_t)enc_save_slot;
+            st.b_enc = b_enc; st.b_save_slot = (int16_t)b_save_slot;
             P.steps.push_back(st);
         };
+
         // one GEMM of n_out (padded) output columns, `valid` of them real, as ceil(n_out / 128) steps
+        uint8_t pending_pre = TS_PRE_NONE;   // set after a GEMM that is the last reader of a slot-E panel: the next step emitted carries the write
         auto emit_gemm = [&](TsProgram &P, const std::vector<KSrc> &kin, int n_out, int valid, uint8_t kind, uint32_t bias_off, int save_slot0,
                              int mask_slot, uint8_t enc, int enc_save_slot, bool writes_a) {
             const bool small = kind == EK_SIGMA || kind == EK_RGBA;
@@ -486,14 +489,19 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 st.bias_off = (uint16_t)(bias_off + 128u * h);
                 st.save_slot = (int16_t)(save_slot0 < 0 ? -1 : save_slot0 + 2 * h);
                 st.mask_slot = (int16_t)mask_slot;
-                st.enc = (h == nh - 1) ? enc : (uint8_t)ENC_NONE;
-                st.enc_save_slot = (int16_t)((h == nh - 1) ? enc_save_slot : -1);
+                (void)enc; (void)enc_save_slot;   // (slot-E panels are written by the pre-encode actions, see mark_pre)
+                st.enc = ENC_NONE;
+                st.enc_save_slot = -1;
                 P.steps.push_back(st);
+                if (pending_pre != TS_PRE_NONE && h == 0) { P.steps.back().pre_enc = pending_pre; pending_pre = TS_PRE_NONE; }
             }
         };
         for (int train = 0; train < 2; ++train) {
             TsProgram &P = train ? plan.ts_fwd_train : plan.ts_fwd_infer;
-            emit_prologue(P, EK_PROLOGUE_FWD, ENC_X, train ? sl.X() : -1);
+            const bool dir = g.use_rgb_head && g.Cd;
+            emit_prologue(P, EK_PROLOGUE_FWD, ENC_X, train ? sl.X() : -1, dir ? ENC_D : ENC_NONE, (dir && train) ? sl.D() : -1);
+            pending_pre = TS_PRE_NONE;
+            const int last_x_layer = g.skip_layer ? g.skip_layer + 1 : 1;   // the last GEMM that reads the encoded positions
             for (int l = 1; l <= 7; ++l) {
                 const LayerGeom &L = g.L[l - 1];
                 const bool skip = g.skip_layer && l == g.skip_layer + 1;
@@ -501,14 +509,13 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 if (l == 1 || skip) kin.push_back({TS_A_SMEM, 4, L.w_off, L.in_dim, 1, g.Cx});
                 if (l > 1) hidden_src(kin, np, L.w_off, L.in_dim, 1, skip ? g.Cx : 0, g.W);
                 emit_gemm(P, kin, g.Wp, g.W, EK_RELU, bias_l[l], train ? sl.H(l) : -1, train ? (l - 1) : -1, ENC_NONE, -1, true);
+                if (l == last_x_layer) pending_pre = TS_PRE_A;   // its successor's epilogue may write the next tile's positions
             }
-            {   // fc8 sigma row, before the feature GEMM's epilogue rewrites h7. Its epilogue also writes the encoded direction
-                // into slot E for fc9 (the skip GEMM fc6, X's last reader, is long done; no first-half stash is live here)
+            {   // fc8 sigma row, before the feature GEMM's epilogue rewrites h7
                 const LayerGeom &L = g.L[7];
                 std::vector<KSrc> kin;
                 hidden_src(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
-                const bool dir = g.use_rgb_head && g.Cd;
-                emit_gemm(P, kin, 32, 1, EK_SIGMA, bias_s, -1, -1, dir ? ENC_D : ENC_NONE, (dir && train) ? sl.D() : -1, false);
+                emit_gemm(P, kin, 32, 1, EK_SIGMA, bias_s, -1, -1, ENC_NONE, -1, false);
             }
             if (g.use_rgb_head) {
                 {
@@ -520,9 +527,10 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                 {
                     const LayerGeom &L = g.L[8];
                     std::vector<KSrc> kin;
-                    if (g.Cd) kin.push_back({TS_A_SMEM, 2, L.w_off + g.W, L.in_dim, 1, g.Cd});
+                    if (g.Cd) kin.push_back({TS_A_SMEM_B, 2, L.w_off + g.W, L.in_dim, 1, g.Cd});
                     hidden_src(kin, np, L.w_off, L.in_dim, 1, 0, g.W);
                     emit_gemm(P, kin, g.W2p, g.W2, EK_RELU, bias_9, train ? sl.h9() : -1, train ? 7 : -1, ENC_NONE, -1, true);
+                    if (g.Cd) pending_pre = TS_PRE_B;   // fc10's epilogue may write the next tile's encoded direction
                 }
                 {
                     const LayerGeom &L = g.L[9];
@@ -535,12 +543,14 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
         {
             TsProgram &P = plan.ts_bwd;
             if (g.use_rgb_head) {
-                emit_prologue(P, EK_PROLOGUE_BWD, ENC_NONE, sl.R());
+                emit_prologue(P, EK_PROLOGUE_BWD, ENC_NONE, sl.R(), ENC_DSIGMA, sl.Sg());
+                pending_pre = TS_PRE_NONE;
                 {   // dH9 = dPre10 (K = 16) * W10 -> mask(h9) -> dPre9
                     const LayerGeom &L = g.L[9];
                     std::vector<KSrc> kin;
                     kin.push_back({TS_A_SMEM, 1, L.w_off, 1, L.in_dim, 4});
-                    emit_gemm(P, kin, g.W2p, g.W2, EK_DMASK, 0, sl.dP9(), 7, ENC_DSIGMA, sl.Sg(), true);
+                    emit_gemm(P, kin, g.W2p, g.W2, EK_DMASK, 0, sl.dP9(), 7, ENC_NONE, -1, true);
+                    pending_pre = TS_PRE_A;
                 }
                 {   // dFeat = dPre9 * W9[:, 0:W]
                     const LayerGeom &L = g.L[8];
@@ -549,14 +559,16 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
                     emit_gemm(P, kin, g.Wp, g.W, EK_DCOPY, 0, sl.dFeat(), -1, ENC_NONE, -1, true);
                 }
             } else {
-                emit_prologue(P, EK_PROLOGUE_BWD, ENC_DSIGMA, sl.Sg());
+                emit_prologue(P, EK_PROLOGUE_BWD, ENC_DSIGMA, sl.Sg(), ENC_NONE, -1);   // (sigma-only network: d(sigma) is panel A)
+                pending_pre = TS_PRE_NONE;
             }
             {   // dH7 = [dsigma | dFeat] * W8 -> mask(h7) -> dPre7
                 const LayerGeom &L = g.L[7];
                 std::vector<KSrc> kin;
-                kin.push_back({TS_A_SMEM, 1, L.w_off, 1, L.in_dim, 1});
+                kin.push_back({g.use_rgb_head ? TS_A_SMEM_B : TS_A_SMEM, 1, L.w_off, 1, L.in_dim, 1});
                 if (g.use_rgb_head) hidden_src(kin, np, L.w_off + L.in_dim, 1, L.in_dim, 0, g.W);
                 emit_gemm(P, kin, g.Wp, g.W, EK_DMASK, 0, sl.dP(7), 6, ENC_NONE, -1, true);
+                pending_pre = g.use_rgb_head ? TS_PRE_B : TS_PRE_A;
             }
             for (int l = 7; l >= 2; --l) {
                 const LayerGeom &L = g.L[l - 1];
