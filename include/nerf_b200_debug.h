@@ -37,6 +37,10 @@ int nerf_debug_host_pose(float yaw, float pitch, float *yaw3x4, float *pitch3x3,
 
 /* Read one saved 16 KB panel image back: area 0 = activations, 1 = pre-activation gradients;
  * area 2 = relu bit masks (slot = mask slot, out = 128*8 uint32). */
+/* the TS-mode chain programs (mlp_tc.h: TsOp, TsStep, PackChunk; steps[0] = tile prologue); program 0 fwd-train, 1 fwd-infer, 2 bwd.
+   UNSUPPORTED for hidden > 256. info: sizeof(TsOp), sizeof(TsStep), sizeof(PackChunk), packed stream bytes */
+int nerf_debug_ts_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *steps, int32_t *n_steps, void *chunks,
+                       int32_t *n_chunks, int32_t *info);
 /* per-CTA cycle counters of the last TS-mode chain launch, [ctas][16] (library built with -DNERF_TC3_STATS; else UNSUPPORTED) */
 int nerf_debug_tc3_stats(uint64_t *out, int32_t ctas);
 /* (tag << 48 | clock) events of CTA 0's MMA thread in the last TS-mode chain launch (same debug build) */

@@ -91,6 +91,7 @@ SIGNATURES = {
     "nerf_debug_trace": (ctypes.c_int, [vp, i32, vp]),
     "nerf_debug_lane_plan": (ctypes.c_int, [vp, i32, vp, vp, vp, vp, vp, vp]),
     "nerf_debug_host_pose": (ctypes.c_int, [f32, f32, vp, vp, vp]),
+    "nerf_debug_ts_plan": (ctypes.c_int, [P(NerfConfig), i32, vp, P(i32), vp, P(i32), vp, P(i32), P(i32)]),
     "nerf_debug_tc3_stats": (ctypes.c_int, [vp, i32]),
     "nerf_debug_tc3_trace": (ctypes.c_int, [vp, i32]),
     "nerf_debug_read_panel": (ctypes.c_int, [vp, i32, i32, i32, vp]),

@@ -157,14 +157,19 @@ __device__ __forceinline__ void epi_half(const float *cbias, const uint32_t (&r)
             asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(sum2));
             w[j2] = (kKind == EK_RELU) ? ptx::pack_bf16x2_relu(v0, v1) : ptx::pack_bf16x2(v0, v1);
         }
-    } else {
-        const uint32_t m = (kKind == EK_DMASK) ? mask : 0xffffffffu;
+    } else if (kKind == EK_DMASK) {
+        // Mask select without predicates (32 predicate-setting LOP3 + FSEL per group serialise on the 7 predicate registers):
+        // shifted left by the pair index P, the mask has feature 2P's bit at bit 15 and feature 2P+1's at bit 31 -- the sign
+        // bits of bytes 1 and 3 -- and PRMT's sign-replicate mode turns them into a 0xffff / 0x0000 mask per bf16 half.
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-            const float v0 = (m & ts_mask_bit(16 * kHalf + 2 * p)) ? __uint_as_float(r[2 * p]) : 0.f;
-            const float v1 = (m & ts_mask_bit(16 * kHalf + 2 * p + 1)) ? __uint_as_float(r[2 * p + 1]) : 0.f;
-            w[p] = ptx::pack_bf16x2(v0, v1);
+            uint32_t sel;
+            asm("prmt.b32 %0, %1, %1, 0xbb99;" : "=r"(sel) : "r"(mask << (8 * kHalf + p)));
+            w[p] = ptx::pack_bf16x2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1])) & sel;
         }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) w[p] = ptx::pack_bf16x2(__uint_as_float(r[2 * p]), __uint_as_float(r[2 * p + 1]));
     }
 }
 

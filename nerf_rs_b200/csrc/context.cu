@@ -1272,6 +1272,25 @@ int nerf_debug_lane_plan(const nerf_config *cfg, int32_t program, void *ops, int
     return NERF_OK;
 }
 
+int nerf_debug_ts_plan(const nerf_config *cfg, int32_t program, void *ops, int32_t *n_ops, void *steps, int32_t *n_steps, void *chunks,
+                       int32_t *n_chunks, int32_t *info) {
+    if (!cfg || !n_ops || !n_steps || !n_chunks) return NERF_ERR_INVALID_ARG;
+    NetGeom g;
+    build_geom(*cfg, g);
+    TcPlan plan;
+    std::string err;
+    if (!tc_build_plan(g, plan, err) || plan.np > 4) return NERF_ERR_UNSUPPORTED;
+    const TsProgram &P = program == 0 ? plan.ts_fwd_train : (program == 1 ? plan.ts_fwd_infer : plan.ts_bwd);
+    if (ops && *n_ops >= (int)P.ops.size()) memcpy(ops, P.ops.data(), P.ops.size() * sizeof(TsOp));
+    if (steps && *n_steps >= (int)P.steps.size()) memcpy(steps, P.steps.data(), P.steps.size() * sizeof(TsStep));
+    if (chunks && *n_chunks >= (int)P.chunks.size()) memcpy(chunks, P.chunks.data(), P.chunks.size() * sizeof(PackChunk));
+    *n_ops = (int)P.ops.size();
+    *n_steps = (int)P.steps.size();
+    *n_chunks = (int)P.chunks.size();
+    if (info) { info[0] = (int)sizeof(TsOp); info[1] = (int)sizeof(TsStep); info[2] = (int)sizeof(PackChunk); info[3] = (int)P.wpack_bytes; }
+    return NERF_OK;
+}
+
 int nerf_debug_plan_biases(const nerf_config *cfg, void *out, int32_t *n) {
     if (!cfg || !n) return NERF_ERR_INVALID_ARG;
     NetGeom g;

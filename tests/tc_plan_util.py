@@ -197,166 +197,3 @@ class Barrier:
 
     def passed(self, parity):
         return (self.phase & 1) != parity
-
-
-def simulate_protocol(plan, n_tiles, rng, max_steps=2_000_000):
-    """Random-interleaving simulation of the producer / MMA / epilogue roles against the mbarrier
-    protocol of k_chain. Raises AssertionError on deadlock, on a read of a stale or too-new slot
-    version, on an accumulator or ring-stage hazard. Returns the number of scheduler steps."""
-    ops, jobs = plan["ops"], plan["jobs"]
-    bars = [Barrier(1) for _ in range(2 * NUM_STAGES)] + [Barrier(1), Barrier(1), Barrier(4), Barrier(4)] + [Barrier(4) for _ in range(3)]
-
-    # ---- logical (sequential) semantics: expected slot / accumulator versions per op and job
-    slot_ver = [0] * NUM_SLOTS
-    acc_ver = [0, 0]
-    op_expect, job_expect_acc, job_writes = [], [], []
-    seq = []  # (tile, 'op'/'job', index)
-    for t in range(n_tiles):
-        ji = 0
-
-        def logical_job(ji):
-            j = jobs[ji]
-            writes = []
-            if j["out_slot"] != NONE and j["kind"] in (EK_RELU, EK_LINEAR, EK_DMASK, EK_DCOPY):
-                for p in range(int(j["ncols"]) // 64):
-                    slot_ver[j["out_slot"] + p] += 1
-                    writes.append((int(j["out_slot"]) + p, slot_ver[j["out_slot"] + p]))
-            if j["kind"] in (EK_PROLOGUE_FWD, EK_PROLOGUE_BWD) or j["enc"] != ENC_NONE:
-                slot_ver[SLOT_E] += 1
-                writes.append((SLOT_E, slot_ver[SLOT_E]))
-            job_writes.append(writes)
-            job_expect_acc.append(acc_ver[j["acc"]] if j["acc"] != NONE else None)
-
-        while ji < len(jobs) and jobs[ji]["acc"] == NONE:
-            logical_job(ji); ji += 1
-        for oi, op in enumerate(ops):
-            if op["flags"] & OP_FIRST:
-                acc_ver[op["acc"]] += 1
-            op_expect.append((slot_ver[op["a_slot"]], acc_ver[op["acc"]]))
-            if op["flags"] & OP_COMMIT:
-                while True:
-                    last = jobs[ji]["flags"] & JOB_RELEASE
-                    logical_job(ji); ji += 1
-                    if last:
-                        break
-                while ji < len(jobs) and jobs[ji]["acc"] == NONE:
-                    logical_job(ji); ji += 1
-        assert ji == len(jobs)
-
-    # ---- concurrent state
-    cur_slot_ver = [0] * NUM_SLOTS
-    cur_acc_ver = [0, 0]       # version being accumulated / last written
-    stage_content = [None] * NUM_STAGES    # global op index whose chunk is in the stage (after load completes)
-    n_total_ops = n_tiles * len(ops)
-    n_total_jobs = n_tiles * len(jobs)
-
-    prod = dict(i=0, stage=0, phase=0)
-    loads = []               # in-flight bulk loads: (stage, global op index)
-    mma = dict(i=0, stage=0, phase=0, wph=(1 << BAR_ACC_FREE) | (1 << (BAR_ACC_FREE + 1)), sub=0)
-    inflight = []            # issued, incomplete MMA ops (FIFO): dict(gi, commits=[bar ids])
-    epi = dict(i=0, aph=0, sub=0)
-    steps = 0
-    while prod["i"] < n_total_ops or mma["i"] < n_total_ops or epi["i"] < n_total_jobs or inflight or loads:
-        steps += 1
-        assert steps < max_steps, "simulation did not terminate"
-        actions = []
-        # producer
-        if prod["i"] < n_total_ops and bars[BAR_EMPTY + prod["stage"]].passed(prod["phase"] ^ 1):
-            actions.append("prod")
-        if loads:
-            actions.append("load_done")
-        # mma
-        if mma["i"] < n_total_ops:
-            op = ops[mma["i"] % len(ops)]
-            ok = True
-            if mma["sub"] == 0:
-                for w in (op["wait0"], op["wait1"]):
-                    if w != NONE and not bars[w].passed((mma["wph"] >> int(w)) & 1):
-                        ok = False
-                if ok and not bars[BAR_FULL + mma["stage"]].passed(mma["phase"]):
-                    ok = False
-            if ok:
-                actions.append("mma")
-        if inflight:
-            actions.append("mma_done")
-        # epilogue
-        if epi["i"] < n_total_jobs:
-            j = jobs[epi["i"] % len(jobs)]
-            if epi["sub"] == 0 and j["acc"] != NONE and (j["flags"] & JOB_WAIT):
-                if bars[BAR_ACC_FULL + j["acc"]].passed((epi["aph"] >> int(j["acc"])) & 1):
-                    actions.append("epi")
-            else:
-                actions.append("epi")
-        assert actions, f"deadlock: prod={prod} mma={mma} epi={epi} inflight={len(inflight)}"
-        a = actions[rng.integers(len(actions))]
-        if a == "prod":
-            st = prod["stage"]
-            # the stage may only be refilled once the op that read it has completed
-            assert stage_content[st] is None or stage_content[st] == "free", "ring stage overwritten while in use"
-            loads.append((st, prod["i"]))
-            stage_content[st] = "loading"
-            prod["i"] += 1
-            prod["stage"] += 1
-            if prod["stage"] == NUM_STAGES:
-                prod["stage"], prod["phase"] = 0, prod["phase"] ^ 1
-        elif a == "load_done":
-            st, gi = loads.pop(rng.integers(len(loads)))
-            stage_content[st] = gi
-            bars[BAR_FULL + st].arrive()
-        elif a == "mma":
-            gi = mma["i"]
-            op = ops[gi % len(ops)]
-            for w in (op["wait0"], op["wait1"]):
-                if w != NONE:
-                    mma["wph"] ^= 1 << int(w)
-            st = mma["stage"]
-            assert stage_content[st] == gi, f"op {gi} found chunk of op {stage_content[st]} in its ring stage"
-            exp_slot, exp_acc = op_expect[gi]
-            assert cur_slot_ver[op["a_slot"]] == exp_slot, f"op {gi}: A slot {op['a_slot']} version {cur_slot_ver[op['a_slot']]} != expected {exp_slot}"
-            if op["flags"] & OP_FIRST:
-                cur_acc_ver[op["acc"]] += 1
-            assert cur_acc_ver[op["acc"]] == exp_acc, f"op {gi}: accumulator version mismatch"
-            commits = [BAR_EMPTY + st]
-            if op["flags"] & OP_COMMIT:
-                commits.append(BAR_ACC_FULL + int(op["acc"]))
-            inflight.append(dict(gi=gi, commits=commits, slot=int(op["a_slot"]), slot_ver=exp_slot, stage=st, acc=int(op["acc"]), acc_ver=exp_acc))
-            mma["i"] += 1
-            mma["stage"] += 1
-            if mma["stage"] == NUM_STAGES:
-                mma["stage"], mma["phase"] = 0, mma["phase"] ^ 1
-        elif a == "mma_done":
-            o = inflight.pop(0)   # tensor-core ops complete in issue order
-            assert cur_slot_ver[o["slot"]] == o["slot_ver"], f"slot {o['slot']} overwritten while op {o['gi']} was reading it"
-            assert cur_acc_ver[o["acc"]] == o["acc_ver"], "accumulator overwritten while an op was accumulating into it"
-            stage_content[o["stage"]] = "free"
-            for b in o["commits"]:
-                bars[b].arrive()
-        elif a == "epi":
-            gj = epi["i"]
-            j = jobs[gj % len(jobs)]
-            if epi["sub"] == 0:
-                if j["acc"] != NONE:
-                    if j["flags"] & JOB_WAIT:
-                        epi["aph"] ^= 1 << int(j["acc"])
-                    assert cur_acc_ver[j["acc"]] == job_expect_acc[gj], f"job {gj}: accumulator version mismatch"
-                    assert not any(o["acc"] == j["acc"] and o["acc_ver"] == job_expect_acc[gj] for o in inflight), "job reads an accumulator with MMAs in flight"
-                    epi["sub"] = 1
-                else:
-                    epi["sub"] = 2
-            elif epi["sub"] == 1:   # accumulator read: release it
-                assert cur_acc_ver[j["acc"]] == job_expect_acc[gj], "accumulator overwritten while the epilogue was reading it"
-                if j["flags"] & JOB_RELEASE:
-                    bars[BAR_ACC_FREE + j["acc"]].arrive(4)
-                epi["sub"] = 2
-            elif epi["sub"] == 2:   # panel writes
-                for slot, ver in job_writes[gj]:
-                    assert not any(o["slot"] == slot for o in inflight), f"job {gj} writes slot {slot} while an MMA reads it"
-                    assert cur_slot_ver[slot] == ver - 1, "slot written out of order"
-                    cur_slot_ver[slot] = ver
-                if j["ready_bar"] != NONE:
-                    bars[j["ready_bar"]].arrive(4)
-                if j["enc_bar"] != NONE:
-                    bars[j["enc_bar"]].arrive(4)
-                epi["sub"] = 0
-                epi["i"] += 1
-    return steps

@@ -111,14 +111,17 @@ def test_bench_synthetic_weights_are_the_survey_init():
 
 def test_built_kernels_contain_the_blackwell_instructions():
     """SASS of the in-tree objects (cuobjdump, no GPU needed): the MLP kernels really issue tcgen05 MMAs (UTCHMMA), commits
-    (UTCBAR), tensor-memory loads (LDTM), bulk async copies (UBLKCP) and packed fp32x2 adds (FADD2); the production chain kernels
-    compile without spills (profiles/r01_trace_notes.md: register hygiene was worth 15 %)."""
+    (UTCBAR), tensor-memory loads (LDTM) and -- the TS-mode chain -- tensor-memory STORES (STTM: the activations are the next
+    layer's A operand in TMEM), bulk async copies (UBLKCP) and packed fp32x2 adds (FADD2); the production chain kernels
+    compile without spills in inference and with at most a handful of spilled words when training
+    (profiles/r01_trace_notes.md: register hygiene was worth 15 %)."""
     import shutil
     import subprocess
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not on PATH")
     build = os.path.join(ROOT, "nerf_rs_b200", "build")
-    want = {"mlp_tc2.cu.o": ["UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "FADD2", "UTCATOMSWS"],
+    want = {"mlp_tc3.cu.o": ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UBLKCP", "FADD2", "UTCATOMSWS"],
+            "mlp_tc2.cu.o": ["UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "FADD2", "UTCATOMSWS"],
             "mlp_tc.cu.o": ["UTCHMMA", "UTCBAR", "LDTM", "UBLKCP", "RED"]}
     for obj, mnemonics in want.items():
         path = os.path.join(build, obj)
@@ -127,14 +130,27 @@ def test_built_kernels_contain_the_blackwell_instructions():
         sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
         for m in mnemonics:
             assert m in sass, f"{m} missing from {obj}"
-    lines = open(os.path.join(build, "mlp_tc2.cu.log")).read().splitlines()
-    narrow = {}
-    for i, ln in enumerate(lines):
-        m = re.search(r"Compiling entry function '(\S+)'", ln)
-        if m and any(k in m.group(1) for k in ("k_chain2ILb0ELb0ELb0ELb0ELb0EE", "k_chain2ILb0ELb1ELb0ELb0ELb0EE", "k_chain2ILb1ELb1ELb0ELb0ELb0EE")):
-            sp = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", " ".join(lines[i:i + 4]))
-            assert sp, lines[i:i + 4]
-            narrow[m.group(1)] = tuple(int(x) for x in sp.groups())
-    assert len(narrow) == 3, list(narrow)          # inference forward, training forward, dgrad (hidden <= 256)
-    for name, (stack, st, ld) in narrow.items():
+
+    def spills(log, names):
+        lines = open(os.path.join(build, log)).read().splitlines()
+        out = {}
+        for i, ln in enumerate(lines):
+            m = re.search(r"Compiling entry function '(\S+)'", ln)
+            if m and any(k in m.group(1) for k in names):
+                sp = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", " ".join(lines[i:i + 4]))
+                assert sp, lines[i:i + 4]
+                out[m.group(1)] = tuple(int(x) for x in sp.groups())
+        return out
+
+    # SS-mode pair kernel (hidden 449..512 and A/B runs): inference forward, training forward, dgrad
+    ss = spills("mlp_tc2.cu.log", ("k_chain2ILb0ELb0ELb0ELb0ELb0EE", "k_chain2ILb0ELb1ELb0ELb0ELb0EE", "k_chain2ILb1ELb1ELb0ELb0ELb0EE"))
+    assert len(ss) == 3, list(ss)
+    for name, (stack, st, ld) in ss.items():
         assert st == 0 and ld == 0, (name, stack, st, ld)
+    # TS-mode kernel: <false,false,false> inference, <false,true,false> training forward, <true,true,false> dgrad
+    ts = spills("mlp_tc3.cu.log", ("k_chain3ILb0ELb0ELb0EE", "k_chain3ILb0ELb1ELb0EE", "k_chain3ILb1ELb1ELb0EE"))
+    assert len(ts) == 3, list(ts)
+    for name, (stack, st, ld) in ts.items():
+        assert stack <= 16 and st <= 32 and ld <= 64, (name, stack, st, ld)
+        if "ILb0ELb0ELb0EE" in name:
+            assert st == 0 and ld == 0, (name, stack, st, ld)
