@@ -133,6 +133,8 @@ struct nerf_ctx {
 
     // timers / scratch
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t ev_stage = nullptr;   // recorded after the asynchronous H2D copies out of the pinned index staging buffer
+    bool stage_busy = false;
     uint8_t *d_flush = nullptr;
     size_t flush_bytes = 0;
     float *d_frame_rgba = nullptr;       // full-frame render targets (lazily allocated)
@@ -589,6 +591,7 @@ int nerf_destroy(nerf_ctx *c) {
     if (c->h_i32) cudaFreeHost(c->h_i32);
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
+    if (c->ev_stage) cudaEventDestroy(c->ev_stage);
     for (auto e : c->prof.pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -640,6 +643,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUB(cudaEventCreate(&c->t0));
     CUB(cudaEventCreate(&c->t1));
+    CUB(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
     const int64_t P = c->g.n_params, Pp = (P + 3) / 4 * 4;
     CUB(cudaMalloc(&c->d_params, sizeof(float) * Pp));
     CUB(cudaMalloc(&c->d_grads, sizeof(float) * Pp));
@@ -808,6 +812,12 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
         return fail(c, NERF_ERR_INVALID_ARG, "get_batch: can't divide rays evenly among views (dataset.rs:73-81)");
     const int n_views = ((c->d_images || c->d_images_u8) && c->n_img_views < c->n_poses) ? c->n_img_views : c->n_poses;
     int rc;
+    if ((indices_yx || view_index) && c->stage_busy) {
+        // the previous call's copies out of the pinned staging buffer are asynchronous: a caller that never reads anything
+        // back can be several batches ahead of the stream, so wait for them before the buffer is rewritten
+        CU(c, cudaEventSynchronize(c->ev_stage));
+        c->stage_busy = false;
+    }
     if (indices_yx) {
         rc = ensure_i32(c, (size_t)2 * R + n_picks);
         if (rc) return rc;
@@ -827,6 +837,10 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
             c->h_i32[2 * R + i] = (int32_t)view_index[i];
         }
         CU(c, cudaMemcpyAsync(c->d_view_pick, c->h_i32 + 2 * R, sizeof(int32_t) * n_picks, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (indices_yx || view_index) {
+        CU(c, cudaEventRecord(c->ev_stage, c->stream));
+        c->stage_busy = true;
     }
     c->gen_pix = indices_yx ? 0 : 1;       // missing picks are drawn inside the sampler (Philox)
     c->gen_view = view_index ? 0 : 1;

@@ -109,7 +109,11 @@ class NeRF {
     // residency from RGBA8 bytes (4 B/pixel on the device; the gold gather does the `as f32 / 255.` of image_loading.rs:13-18)
     void set_images_rgba8(const std::vector<std::vector<uint8_t>> &imgs) {
         std::vector<uint8_t> flat;
-        for (auto &im : imgs) flat.insert(flat.end(), im.begin(), im.end());
+        for (auto &im : imgs) {
+            // a decoded file of another size than the context's image_w x image_h must not reach the device copy
+            if (im.size() != (size_t)cfg_.image_w * cfg_.image_h * 4) throw std::runtime_error("set_images_rgba8: image size differs from the configuration");
+            flat.insert(flat.end(), im.begin(), im.end());
+        }
         check(ctx_, nerf_set_images_rgba8(ctx_, flat.data(), (int32_t)imgs.size()));
         n_views_ = (int)imgs.size();
     }

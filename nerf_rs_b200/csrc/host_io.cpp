@@ -24,7 +24,18 @@ int paeth(int a, int b, int c) {
 
 }  // namespace
 
+static int load_png_rgba8(const char *path, uint8_t *out, int64_t capacity_bytes, int32_t *width, int32_t *height);
+
+// Nothing may be thrown across the C ABI (a crafted or truncated file must not terminate the Rust / ctypes caller).
 extern "C" int nerf_load_png_rgba8(const char *path, uint8_t *out, int64_t capacity_bytes, int32_t *width, int32_t *height) {
+    try {
+        return load_png_rgba8(path, out, capacity_bytes, width, height);
+    } catch (...) {   // std::bad_alloc, std::length_error
+        return NERF_ERR_INVALID_ARG;
+    }
+}
+
+static int load_png_rgba8(const char *path, uint8_t *out, int64_t capacity_bytes, int32_t *width, int32_t *height) {
     if (!path || !width || !height) return NERF_ERR_INVALID_ARG;
     FILE *f = fopen(path, "rb");
     if (!f) return NERF_ERR_INVALID_ARG;
@@ -51,7 +62,8 @@ extern "C" int nerf_load_png_rgba8(const char *path, uint8_t *out, int64_t capac
         }
         pos += 12 + (size_t)len;
     }
-    if (w == 0 || h == 0) return NERF_ERR_INVALID_ARG;
+    // IHDR is untrusted: bound the dimensions before any size arithmetic or allocation (65535^2 * 4 fits size_t comfortably)
+    if (w == 0 || h == 0 || w > 65535u || h > 65535u) return NERF_ERR_INVALID_ARG;
     *width = (int32_t)w;
     *height = (int32_t)h;
     if (depth != 8 || ctype != 6 || interlace != 0) return NERF_ERR_UNSUPPORTED;   // not ImageData::RGBA8

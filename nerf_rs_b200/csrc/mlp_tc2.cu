@@ -348,11 +348,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) k_chain
                             // the host->device copy of the points runs on another stream, chunk by chunk: wait until the chunk
                             // holding this sample has landed (the copy engine writes the counter after the chunk, in stream order)
                             const unsigned int need = (unsigned int)(gs / a.h2d_chunk_samples) + 1u;
-                            unsigned int spins = 0;
-                            while (*reinterpret_cast<const volatile unsigned int *>(a.h2d_flag) < need) {
+                            unsigned int spins = 0, have;
+                            do {   // acquire: the point loads below may not be satisfied before the counter is seen
+                                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(a.h2d_flag) : "memory");
+                                if (have >= need) break;
                                 __nanosleep(256);
-                                if (++spins > (1u << 24)) __trap();   // the host copy never arrived
-                            }
+                            } while (++spins < (1u << 24));
+                            if (have < need) __trap();   // the host copy never arrived
                             v[0] = __ldcg(a.points + 3 * gs); v[1] = __ldcg(a.points + 3 * gs + 1); v[2] = __ldcg(a.points + 3 * gs + 2);
                         } else {
                             v[0] = a.points[3 * gs]; v[1] = a.points[3 * gs + 1]; v[2] = a.points[3 * gs + 2];
