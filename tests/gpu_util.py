@@ -51,3 +51,8 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+def bf16_round(a):
+    """float32 -> nearest-even bfloat16 -> float32 (what cvt.rn.bf16x2.f32 does)."""
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(torch.bfloat16).to(torch.float32).numpy()

@@ -109,6 +109,15 @@ def test_step_gradients_loss_and_adam(name, impl):
             continue
         err = np.linalg.norm(g[a:b] - ref) / np.linalg.norm(ref)
         assert err < tol, f"fc{li + 1}: relative gradient error {err:.3e}"
+    if not fp32:
+        # the same gradient against pure fp32 autograd (the reference's arithmetic), reported and bounded
+        tr32 = M.Trainer(mcfg, params_t, lr=5e-4)
+        o32, _ = tr32.predict(torch.from_numpy(pts), torch.from_numpy(t), r, s, torch.from_numpy(dirs) if mcfg.cd else None, literal=False)
+        tr32.step(o32, torch.from_numpy(gold))
+        g32 = tr32.grads_flat().numpy()
+        errs = [float(np.linalg.norm(g[a:b] - g32[a:b]) / np.linalg.norm(g32[a:b])) for a, b in _layer_slices(mcfg) if np.abs(g32[a:b]).max() > 0]
+        print(f"{name}: per-layer gradient error vs the fp32 oracle", [f"{e:.2e}" for e in errs])
+        assert max(errs) < 8e-2
     # Adam (model.rs:306-309, 322): the update applied to the kernel's own gradient is exact
     p1, _, _ = M.adam_reference(torch.from_numpy(w0), torch.from_numpy(g), torch.zeros(g.size), torch.zeros(g.size), 1)
     w1 = m.get_weights()
