@@ -93,7 +93,9 @@ int nerf_abi_version(void);
 int64_t nerf_num_params(const nerf_ctx *ctx);
 int nerf_set_weights(nerf_ctx *ctx, const float *flat, int64_t n);
 int nerf_get_weights(nerf_ctx *ctx, float *flat, int64_t n);
-int nerf_get_grads(nerf_ctx *ctx, float *flat, int64_t n);          /* d(loss)/d(param) of the last step */
+/* d(loss)/d(param) of the last step. With a communicator: the SUM over the ranks of their local gradients (what the
+ * all-reduce produced); the update applied was that sum / nranks = the gradient of the concatenated batch's mean loss. */
+int nerf_get_grads(nerf_ctx *ctx, float *flat, int64_t n);
 int nerf_get_adam_state(nerf_ctx *ctx, float *m, float *v, int64_t n, int64_t *step);
 int nerf_set_adam_state(nerf_ctx *ctx, const float *m, const float *v, int64_t n, int64_t step);
 
@@ -150,7 +152,9 @@ int nerf_compositing(nerf_ctx *ctx, const float *densities, const float *colors,
 /* ---- Trainer::step (src/model.rs:311-325) -------------------------------------------
  * gold [R*4] host RGBA, or NULL to use the gold gathered by nerf_get_batch.
  * Runs MSE (model.rs:296-299) + backward + Adam. loss may be NULL (no host sync);
- * otherwise the call blocks for the scalar like f32::try_from(&loss) (model.rs:324). */
+ * otherwise the call blocks for the scalar like f32::try_from(&loss) (model.rs:324).
+ * With a communicator the loss (here and in nerf_last_loss) is the RANK-LOCAL mean over this rank's R*4 elements;
+ * the global-batch loss is the mean of the ranks' values. */
 int nerf_step(nerf_ctx *ctx, const float *gold, int64_t n_gold, float *loss);
 
 /* Whole iteration without host round trips: get_batch (Philox) -> predict -> step.
