@@ -45,6 +45,9 @@ int nerf_debug_ts_plan(const nerf_config *cfg, int32_t program, void *ops, int32
 int nerf_debug_tc3_stats(uint64_t *out, int32_t ctas);
 /* (tag << 48 | clock) events of CTA 0's MMA thread in the last TS-mode chain launch (same debug build) */
 int nerf_debug_tc3_trace(uint64_t *out, int32_t n);
+/* NERF_B200_GUARD=1 (read once, before the first allocation): every device buffer gets guard bands and a NaN fill
+   (csrc/guard.h). Returns the number of allocations whose bands were overwritten (0 = clean), -1 when the mode is off. */
+int nerf_debug_check_guards(int32_t *n_allocations);
 int nerf_debug_read_panel(nerf_ctx *ctx, int32_t area, int32_t tile, int32_t slot, void *out);
 
 /* Run one chain program (0 forward-train, 1 forward-inference, 2 backward dgrad) on the resident

@@ -94,6 +94,7 @@ SIGNATURES = {
     "nerf_debug_ts_plan": (ctypes.c_int, [P(NerfConfig), i32, vp, P(i32), vp, P(i32), vp, P(i32), P(i32)]),
     "nerf_debug_tc3_stats": (ctypes.c_int, [vp, i32]),
     "nerf_debug_tc3_trace": (ctypes.c_int, [vp, i32]),
+    "nerf_debug_check_guards": (ctypes.c_int, [P(i32)]),
     "nerf_debug_read_panel": (ctypes.c_int, [vp, i32, i32, i32, vp]),
     "nerf_debug_wgrad_partition": (ctypes.c_int, [P(NerfConfig), i32, i64, vp, vp, P(i32)]),
     "nerf_debug_wgrad_marks": (ctypes.c_int, [vp, vp, i32]),

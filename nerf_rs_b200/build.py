@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libnerf_b200.so")
-SOURCES = ["context.cu", "sampling.cu", "composite.cu", "adam.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc3.cu", "mlp_tc_plan.cpp", "comm.cpp", "host_io.cpp", "metrics.cu"]
+SOURCES = ["context.cu", "sampling.cu", "composite.cu", "adam.cu", "mlp_simt.cu", "mlp_tc.cu", "mlp_tc2.cu", "mlp_tc3.cu", "mlp_tc_plan.cpp", "comm.cpp", "host_io.cpp", "metrics.cu", "guard.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off", "-Xptxas", "-v",

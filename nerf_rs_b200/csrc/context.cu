@@ -16,6 +16,7 @@
 #include "../../include/nerf_b200.h"
 #include "../../include/nerf_b200_debug.h"
 #include "comm.h"
+#include "guard.h"
 #include "kernels.h"
 #include "mlp_tc.h"
 
@@ -579,12 +580,12 @@ int nerf_destroy(nerf_ctx *c) {
                     c->d_rays, c->d_dirs, c->d_t, c->d_points, c->d_gold, c->d_jitter, c->d_sigma, c->d_rgba, c->d_out,
                     c->d_dsigma, c->d_drgba, c->d_loss_partials, c->d_loss, c->simt.x_enc, c->simt.d_enc, c->simt.act, c->simt.dact,
                     c->d_flush, c->d_frame_rgba, c->d_frame_0rgb, c->d_gacc[0], c->d_gacc[1], c->d_images_u8, c->d_metrics};
-    for (void *p : ptrs) cudaFree(p);
+    for (void *p : ptrs) guard_free(p);
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
         cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_dirs); cudaEventDestroy(c->ev_all);
-        cudaFree(c->d_h2d_flag);
+        guard_free(c->d_h2d_flag);
         cudaFreeHost(c->h_h2d_seq);
     }
     if (c->h_loss) cudaFreeHost(c->h_loss);
@@ -645,31 +646,31 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     CUB(cudaEventCreate(&c->t1));
     CUB(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
     const int64_t P = c->g.n_params, Pp = (P + 3) / 4 * 4;
-    CUB(cudaMalloc(&c->d_params, sizeof(float) * Pp));
-    CUB(cudaMalloc(&c->d_grads, sizeof(float) * Pp));
-    CUB(cudaMalloc(&c->d_m, sizeof(float) * Pp));
-    CUB(cudaMalloc(&c->d_v, sizeof(float) * Pp));
+    CUB(guard_malloc(&c->d_params, sizeof(float) * Pp));
+    CUB(guard_malloc(&c->d_grads, sizeof(float) * Pp));
+    CUB(guard_malloc(&c->d_m, sizeof(float) * Pp));
+    CUB(guard_malloc(&c->d_v, sizeof(float) * Pp));
     CUB(cudaMemsetAsync(c->d_params, 0, sizeof(float) * Pp, c->stream));
     CUB(cudaMemsetAsync(c->d_grads, 0, sizeof(float) * Pp, c->stream));
     CUB(cudaMemsetAsync(c->d_m, 0, sizeof(float) * Pp, c->stream));
     CUB(cudaMemsetAsync(c->d_v, 0, sizeof(float) * Pp, c->stream));
     const int64_t R = c->R, B = c->B;
-    CUB(cudaMalloc(&c->d_pix, sizeof(int32_t) * 2 * R));
-    CUB(cudaMalloc(&c->d_view_pick, sizeof(int32_t) * R));
-    CUB(cudaMalloc(&c->d_rays, sizeof(RayRec) * R));
-    CUB(cudaMalloc(&c->d_dirs, sizeof(float) * 3 * R));
-    CUB(cudaMalloc(&c->d_t, sizeof(float) * B));
-    CUB(cudaMalloc(&c->d_points, sizeof(float) * 3 * B));
-    CUB(cudaMalloc(&c->d_gold, sizeof(float) * 4 * R));
-    CUB(cudaMalloc(&c->d_jitter, sizeof(float) * B));
-    CUB(cudaMalloc(&c->d_sigma, sizeof(float) * B));
-    CUB(cudaMalloc(&c->d_rgba, sizeof(float) * 4 * B));
-    CUB(cudaMalloc(&c->d_out, sizeof(float) * 4 * R));
-    CUB(cudaMalloc(&c->d_dsigma, sizeof(float) * B));
-    CUB(cudaMalloc(&c->d_drgba, sizeof(float) * 4 * B));
-    CUB(cudaMalloc(&c->d_loss_partials, sizeof(float) * (2 * (size_t)R + 16)));   // per-block loss partials: <= ceil(nr/8) per launch
-    CUB(cudaMalloc(&c->d_loss, sizeof(float) * 4));
-    CUB(cudaMalloc(&c->d_render_pose, sizeof(ViewPose)));
+    CUB(guard_malloc(&c->d_pix, sizeof(int32_t) * 2 * R));
+    CUB(guard_malloc(&c->d_view_pick, sizeof(int32_t) * R));
+    CUB(guard_malloc(&c->d_rays, sizeof(RayRec) * R));
+    CUB(guard_malloc(&c->d_dirs, sizeof(float) * 3 * R));
+    CUB(guard_malloc(&c->d_t, sizeof(float) * B));
+    CUB(guard_malloc(&c->d_points, sizeof(float) * 3 * B));
+    CUB(guard_malloc(&c->d_gold, sizeof(float) * 4 * R));
+    CUB(guard_malloc(&c->d_jitter, sizeof(float) * B));
+    CUB(guard_malloc(&c->d_sigma, sizeof(float) * B));
+    CUB(guard_malloc(&c->d_rgba, sizeof(float) * 4 * B));
+    CUB(guard_malloc(&c->d_out, sizeof(float) * 4 * R));
+    CUB(guard_malloc(&c->d_dsigma, sizeof(float) * B));
+    CUB(guard_malloc(&c->d_drgba, sizeof(float) * 4 * B));
+    CUB(guard_malloc(&c->d_loss_partials, sizeof(float) * (2 * (size_t)R + 16)));   // per-block loss partials: <= ceil(nr/8) per launch
+    CUB(guard_malloc(&c->d_loss, sizeof(float) * 4));
+    CUB(guard_malloc(&c->d_render_pose, sizeof(ViewPose)));
     CUB(cudaMemsetAsync(c->d_gold, 0, sizeof(float) * 4 * R, c->stream));
     CUB(cudaMemsetAsync(c->d_rgba, 0, sizeof(float) * 4 * B, c->stream));
     CUB(cudaMemsetAsync(c->d_drgba, 0, sizeof(float) * 4 * B, c->stream));
@@ -683,10 +684,10 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     } else {
         const int64_t bc = (int64_t)c->chunk * c->S;
         c->simt.act_stride = bc * (int64_t)simt_act_floats_per_sample(c->g);
-        CUB(cudaMalloc(&c->simt.x_enc, sizeof(float) * bc * c->g.Cx));
-        CUB(cudaMalloc(&c->simt.d_enc, sizeof(float) * (int64_t)c->chunk * (c->g.Cd > 0 ? c->g.Cd : 1)));
-        CUB(cudaMalloc(&c->simt.act, sizeof(float) * c->simt.act_stride * 9));
-        CUB(cudaMalloc(&c->simt.dact, sizeof(float) * c->simt.act_stride * 3));
+        CUB(guard_malloc(&c->simt.x_enc, sizeof(float) * bc * c->g.Cx));
+        CUB(guard_malloc(&c->simt.d_enc, sizeof(float) * (int64_t)c->chunk * (c->g.Cd > 0 ? c->g.Cd : 1)));
+        CUB(guard_malloc(&c->simt.act, sizeof(float) * c->simt.act_stride * 9));
+        CUB(guard_malloc(&c->simt.dact, sizeof(float) * c->simt.act_stride * 3));
         c->simt_ready = true;
     }
 #undef CUB
@@ -745,9 +746,9 @@ int nerf_set_images(nerf_ctx *c, const float *rgba, int32_t n_views) {
     CU(c, cudaSetDevice(c->device));
     const size_t bytes = sizeof(float) * 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
     CU(c, cudaStreamSynchronize(c->stream));
-    if (c->d_images) { cudaFree(c->d_images); c->d_images = nullptr; }
-    if (c->d_images_u8) { cudaFree(c->d_images_u8); c->d_images_u8 = nullptr; }
-    CU(c, cudaMalloc(&c->d_images, bytes));
+    if (c->d_images) { guard_free(c->d_images); c->d_images = nullptr; }
+    if (c->d_images_u8) { guard_free(c->d_images_u8); c->d_images_u8 = nullptr; }
+    CU(c, guard_malloc(&c->d_images, bytes));
     CU(c, cudaMemcpyAsync(c->d_images, rgba, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->n_img_views = n_views;
@@ -759,9 +760,9 @@ int nerf_set_images_rgba8(nerf_ctx *c, const uint8_t *rgba8, int32_t n_views) {
     CU(c, cudaSetDevice(c->device));
     const size_t bytes = 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
     CU(c, cudaStreamSynchronize(c->stream));
-    if (c->d_images) { cudaFree(c->d_images); c->d_images = nullptr; }
-    if (c->d_images_u8) { cudaFree(c->d_images_u8); c->d_images_u8 = nullptr; }
-    CU(c, cudaMalloc(&c->d_images_u8, bytes));
+    if (c->d_images) { guard_free(c->d_images); c->d_images = nullptr; }
+    if (c->d_images_u8) { guard_free(c->d_images_u8); c->d_images_u8 = nullptr; }
+    CU(c, guard_malloc(&c->d_images_u8, bytes));
     CU(c, cudaMemcpyAsync(c->d_images_u8, rgba8, bytes, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->n_img_views = n_views;
@@ -773,8 +774,8 @@ int nerf_set_view_angles(nerf_ctx *c, const float *yaw_pitch, int32_t n) {
     CU(c, cudaSetDevice(c->device));
     std::vector<ViewPose> poses((size_t)n);
     for (int i = 0; i < n; ++i) make_pose(yaw_pitch[2 * i], yaw_pitch[2 * i + 1], poses[i]);
-    if (c->d_poses) { CU(c, cudaStreamSynchronize(c->stream)); cudaFree(c->d_poses); c->d_poses = nullptr; }
-    CU(c, cudaMalloc(&c->d_poses, sizeof(ViewPose) * (size_t)n));
+    if (c->d_poses) { CU(c, cudaStreamSynchronize(c->stream)); guard_free(c->d_poses); c->d_poses = nullptr; }
+    CU(c, guard_malloc(&c->d_poses, sizeof(ViewPose) * (size_t)n));
     CU(c, cudaMemcpyAsync(c->d_poses, poses.data(), sizeof(ViewPose) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->n_poses = n;
@@ -908,7 +909,7 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
         CU(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
         CU(c, cudaEventCreateWithFlags(&c->ev_all, cudaEventDisableTiming));
-        CU(c, cudaMalloc(&c->d_h2d_flag, sizeof(unsigned int)));
+        CU(c, guard_malloc(&c->d_h2d_flag, sizeof(unsigned int)));
         CU(c, cudaMallocHost(&c->h_h2d_seq, sizeof(unsigned int) * kChunks));
         for (int k = 0; k < kChunks; ++k) c->h_h2d_seq[k] = (unsigned int)k + 1u;
     }
@@ -947,10 +948,10 @@ int nerf_compositing(nerf_ctx *c, const float *densities, const float *colors, c
     if (num_rays < 1 || num_samples < 1 || num_samples > 256) return fail(c, NERF_ERR_INVALID_ARG, "compositing: bad shape");
     const size_t n = (size_t)num_rays * num_samples;
     float *ds = nullptr, *dc = nullptr, *dd = nullptr, *dout = nullptr;
-    CU(c, cudaMalloc(&ds, sizeof(float) * n));
-    CU(c, cudaMalloc(&dd, sizeof(float) * n));
-    CU(c, cudaMalloc(&dout, sizeof(float) * 4 * num_rays));
-    if (colors) CU(c, cudaMalloc(&dc, sizeof(float) * 4 * n));
+    CU(c, guard_malloc(&ds, sizeof(float) * n));
+    CU(c, guard_malloc(&dd, sizeof(float) * n));
+    CU(c, guard_malloc(&dout, sizeof(float) * 4 * num_rays));
+    if (colors) CU(c, guard_malloc(&dc, sizeof(float) * 4 * n));
     CU(c, cudaMemcpyAsync(ds, densities, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(dd, distances, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     if (colors) CU(c, cudaMemcpyAsync(dc, colors, sizeof(float) * 4 * n, cudaMemcpyHostToDevice, c->stream));
@@ -964,7 +965,7 @@ int nerf_compositing(nerf_ctx *c, const float *densities, const float *colors, c
     }
     CU(c, cudaMemcpyAsync(out, dout, sizeof(float) * 4 * num_rays, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    cudaFree(ds); cudaFree(dd); cudaFree(dout); cudaFree(dc);
+    guard_free(ds); guard_free(dd); guard_free(dout); guard_free(dc);
     return check_launch(c, "compositing");
 }
 
@@ -1007,8 +1008,8 @@ int nerf_sync(nerf_ctx *c) {
 static int render_rows_device(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed, bool pack) {
     const int W = c->cfg.image_w, H = c->cfg.image_h;
     if (!c->d_frame_rgba) {
-        CU(c, cudaMalloc(&c->d_frame_rgba, sizeof(float) * 4 * (size_t)W * H));
-        CU(c, cudaMalloc(&c->d_frame_0rgb, sizeof(uint32_t) * (size_t)W * H));
+        CU(c, guard_malloc(&c->d_frame_rgba, sizeof(float) * 4 * (size_t)W * H));
+        CU(c, guard_malloc(&c->d_frame_0rgb, sizeof(uint32_t) * (size_t)W * H));
     }
     ViewPose vp;
     make_pose(yaw, pitch, vp);
@@ -1102,7 +1103,7 @@ int nerf_log_metrics(nerf_ctx *c, const nerf_metrics *m) {
     const size_t off_pkeys = off_dkeys + 30000 * 8;
     const size_t off_res = off_pkeys + (size_t)W * H * 8;
     const size_t total = off_res + (30000 + (size_t)W * H) * 4;
-    if (!c->d_metrics) CU(c, cudaMalloc(&c->d_metrics, total));
+    if (!c->d_metrics) CU(c, guard_malloc(&c->d_metrics, total));
     uint8_t *base = c->d_metrics;
     CU(c, cudaMemsetAsync(base, 0, off_res, c->stream));
     MetricsArgs a;
@@ -1172,7 +1173,7 @@ int nerf_comm_init_rank(nerf_ctx *c, const void *id128, int32_t rank, int32_t nr
     if (nranks > 1 && nranks <= NERF_MAX_RANKS && !(env && env[0] == '0')) {
         const size_t bytes = sizeof(float) * ((c->g.n_params + 3) / 4 * 4);
         for (int b = 0; b < 2; ++b) {
-            if (!c->d_gacc[b]) CU(c, cudaMalloc(&c->d_gacc[b], bytes));
+            if (!c->d_gacc[b]) CU(c, cudaMalloc(&c->d_gacc[b], bytes));   // (plain: the IPC export needs the allocation base)
             CU(c, cudaMemsetAsync(c->d_gacc[b], 0, bytes, c->stream));
         }
         if (comm_p2p_setup(c->comm, c->d_gacc[0], c->d_gacc[1], c->stream, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
@@ -1229,7 +1230,7 @@ int nerf_flush_l2(nerf_ctx *c) {
     CU(c, cudaSetDevice(c->device));
     if (!c->d_flush) {
         c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
-        CU(c, cudaMalloc(&c->d_flush, c->flush_bytes));
+        CU(c, guard_malloc(&c->d_flush, c->flush_bytes));
     }
     CU(c, cudaMemsetAsync(c->d_flush, (int)(c->launch_count & 0xff), c->flush_bytes, c->stream));
     return NERF_OK;
@@ -1351,6 +1352,13 @@ int nerf_debug_tc3_trace(uint64_t *out, int32_t n) {
     return rc == 0 ? NERF_OK : (rc == -1 ? NERF_ERR_UNSUPPORTED : NERF_ERR_CUDA);
 }
 
+int nerf_debug_check_guards(int32_t *n_allocations) {
+    int n = 0;
+    const int bad = guard_check(&n);
+    if (n_allocations) *n_allocations = n;
+    return bad;   // -1: guard mode off (NERF_B200_GUARD=1 was not set when the library first allocated)
+}
+
 int nerf_debug_read_panel(nerf_ctx *c, int32_t area, int32_t tile, int32_t slot, void *out) {
     if (!c || !out) return NERF_ERR_INVALID_ARG;
     if (!c->tc) return fail(c, NERF_ERR_STATE, "debug_read_panel: not a tcgen05 context");
@@ -1384,11 +1392,11 @@ int nerf_debug_bench_stage(nerf_ctx *c, int32_t stage, int32_t num_rays, int32_t
     std::vector<void *> bufs;
     auto alloc = [&](size_t bytes) -> void * {
         void *p = nullptr;
-        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+        if (guard_malloc(&p, bytes) != cudaSuccess) return nullptr;
         bufs.push_back(p);
         return p;
     };
-    auto release = [&]() { for (void *p : bufs) cudaFree(p); };
+    auto release = [&]() { for (void *p : bufs) guard_free(p); };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 
+#include "guard.h"
 #include "kernels.h"
 #include "mlp_tc.h"
 #include "ptx.cuh"
@@ -471,7 +472,7 @@ template <typename T>
 T *upload(const std::vector<T> &v) {
     T *d = nullptr;
     if (v.empty()) return nullptr;
-    if (cudaMalloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
+    if (guard_malloc(&d, v.size() * sizeof(T)) != cudaSuccess) return nullptr;
     cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
     return d;
 }
@@ -508,7 +509,7 @@ struct TcState {
 static bool upload_stream(const std::vector<PackChunk> &chunks, uint32_t bytes, DevStream &d) {
     d.n_chunks = (int)chunks.size();
     d.chunks = upload(chunks);
-    return d.chunks && cudaMalloc(&d.wpack, bytes) == cudaSuccess;
+    return d.chunks && guard_malloc(&d.wpack, bytes) == cudaSuccess;
 }
 
 // version: 0 = best for the geometry (TS mode for hidden <= 256, SS mode above), 2 = SS mode, 3 = TS mode
@@ -534,12 +535,12 @@ TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version
     s->d_pbias = upload(s->plan.biases);
     s->d_units = upload(s->plan.units);
     ok = ok && s->d_pbias && s->d_units;
-    ok = ok && cudaMalloc(&s->d_bias, sizeof(float) * s->plan.bias_floats) == cudaSuccess;
-    ok = ok && cudaMalloc(&s->d_work, sizeof(WgradWork) * (size_t)num_sms) == cudaSuccess;
+    ok = ok && guard_malloc(&s->d_bias, sizeof(float) * s->plan.bias_floats) == cudaSuccess;
+    ok = ok && guard_malloc(&s->d_work, sizeof(WgradWork) * (size_t)num_sms) == cudaSuccess;
     if (max_tiles > 0) {
-        ok = ok && cudaMalloc(&s->d_act, (size_t)max_tiles * s->plan.act_slots * kSlotBytes) == cudaSuccess;
-        ok = ok && cudaMalloc(&s->d_grad, (size_t)max_tiles * s->plan.grad_slots * kSlotBytes) == cudaSuccess;
-        ok = ok && cudaMalloc(&s->d_mask, (size_t)max_tiles * s->plan.mask_slots * NERF_TILE_M * s->plan.mask_words * sizeof(uint32_t)) == cudaSuccess;
+        ok = ok && guard_malloc(&s->d_act, (size_t)max_tiles * s->plan.act_slots * kSlotBytes) == cudaSuccess;
+        ok = ok && guard_malloc(&s->d_grad, (size_t)max_tiles * s->plan.grad_slots * kSlotBytes) == cudaSuccess;
+        ok = ok && guard_malloc(&s->d_mask, (size_t)max_tiles * s->plan.mask_slots * NERF_TILE_M * s->plan.mask_words * sizeof(uint32_t)) == cudaSuccess;
     }
     ok = ok && cudaFuncSetAttribute(k_wgrad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(k_wgrad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem) == cudaSuccess;
@@ -570,16 +571,16 @@ TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version
 void tc_destroy(TcState *s) {
     if (!s) return;
     for (DevStream *d : {&s->fwd, &s->bwd}) {
-        cudaFree(d->chunks);
-        cudaFree(d->wpack);
+        guard_free(d->chunks);
+        guard_free(d->wpack);
     }
-    cudaFree(s->d_pbias);
-    cudaFree(s->d_bias);
-    cudaFree(s->d_units);
-    cudaFree(s->d_work);
-    cudaFree(s->d_act);
-    cudaFree(s->d_grad);
-    cudaFree(s->d_mask);
+    guard_free(s->d_pbias);
+    guard_free(s->d_bias);
+    guard_free(s->d_units);
+    guard_free(s->d_work);
+    guard_free(s->d_act);
+    guard_free(s->d_grad);
+    guard_free(s->d_mask);
     tc2_bias_release(s);
     tc3_bias_release(s);
     tc2_free(s->fwd_train2);
@@ -743,16 +744,16 @@ int tc_debug_trace(TcState *s, const float *points, const float *dirs, int64_t n
     if (n_tiles == 0 || (program != 1 && n_tiles > s->max_tiles) || s->version != 2) return -1;
     unsigned long long *d_trace = nullptr;
     const size_t bytes = sizeof(unsigned long long) * 3 * 2048 * 4;
-    if (cudaMalloc(&d_trace, bytes) != cudaSuccess) return -2;
+    if (guard_malloc(&d_trace, bytes) != cudaSuccess) return -2;
     cudaMemsetAsync(d_trace, 0, bytes, st);
     Chain2Launch l;
-    if (!chain_launch(s, program, l, n, S, st)) { cudaFree(d_trace); return -1; }
+    if (!chain_launch(s, program, l, n, S, st)) { guard_free(d_trace); return -1; }
     l.points = points; l.dirs = dirs; l.sigma = sigma_out; l.rgba = program == 2 ? const_cast<float *>(rgba) : rgba_out;
     l.d_sigma = d_sigma; l.d_rgba = d_rgba;
     l.trace = d_trace;
     chain_run(s, program, l, st);
     cudaMemcpyAsync(host_out, d_trace, bytes, cudaMemcpyDeviceToHost, st);
     const cudaError_t e2 = cudaStreamSynchronize(st);
-    cudaFree(d_trace);
+    guard_free(d_trace);
     return e2 == cudaSuccess ? 0 : -2;
 }
