@@ -337,6 +337,7 @@ def main():
     ap.add_argument("--samples", type=int, default=S)
     ap.add_argument("--rays", type=int, default=R)
     ap.add_argument("--hidden", type=int, default=W, help="512 = BASELINE configs[4] width")
+    ap.add_argument("--deterministic", action="store_true", help="nerf_config.deterministic_grads = 1 (fixed-order weight-gradient reduction)")
     ap.add_argument("--mlp-impl", type=int, default=0, help="A/B only: 3 = the SS-mode chain kernel at every width (NERF_MLP_TCGEN05_SS)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -351,7 +352,8 @@ def main():
     W = args.hidden
     peaks_ = peaks()
     hbm, tf_burst, tf_sus, how = peaks_
-    model, cfg = h.make_model(nb, image_w=IMG, image_h=IMG, num_rays=rays, num_samples=samples, hidden=W, mlp_impl=args.mlp_impl)
+    model, cfg = h.make_model(nb, image_w=IMG, image_h=IMG, num_rays=rays, num_samples=samples, hidden=W, mlp_impl=args.mlp_impl,
+                                deterministic_grads=1 if args.deterministic else 0)
     angles = nb.get_view_angles(N_VIEW_GRID)
     n_views = angles.shape[0]
     imgs = synthetic_images(n_views)

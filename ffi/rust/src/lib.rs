@@ -39,6 +39,7 @@ pub mod sys {
         pub beta1: f32,
         pub beta2: f32,
         pub eps: f32,
+        pub deterministic_grads: i32,
     }
 
     #[repr(C)]

@@ -74,6 +74,8 @@ typedef struct nerf_config {
     int32_t max_rays_per_launch;  /* micro-batch bound for saved activations; 0 = auto */
     float learning_rate;          /* cli.rs:64-65, 5e-4 */
     float beta1, beta2, eps;      /* nn::Adam::default(): .9, .999, 1e-8 (model.rs:307) */
+    int32_t deterministic_grads;  /* 1: weight gradients are reduced in a fixed order (per-segment partial blocks + one reduction
+                                     pass) instead of with fp32 atomics: bit-identical gradients run to run, ~1 % slower */
 } nerf_config;
 
 int nerf_default_config(nerf_config *cfg);

@@ -27,6 +27,7 @@ class NerfConfig(ctypes.Structure):
         ("skip_layer", ctypes.c_int32), ("use_rgb_head", ctypes.c_int32), ("sigma_relu", ctypes.c_int32),
         ("depth_mode", ctypes.c_int32), ("mlp_impl", ctypes.c_int32), ("max_rays_per_launch", ctypes.c_int32),
         ("learning_rate", ctypes.c_float), ("beta1", ctypes.c_float), ("beta2", ctypes.c_float), ("eps", ctypes.c_float),
+        ("deterministic_grads", ctypes.c_int32),
     ]
 
 

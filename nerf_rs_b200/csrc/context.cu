@@ -541,6 +541,7 @@ int nerf_default_config(nerf_config *cfg) {
     cfg->mlp_impl = NERF_MLP_TCGEN05;
     cfg->max_rays_per_launch = 0;
     cfg->learning_rate = 5e-4f; cfg->beta1 = 0.9f; cfg->beta2 = 0.999f; cfg->eps = 1e-8f;
+    cfg->deterministic_grads = 0;
     return NERF_OK;
 }
 
@@ -679,7 +680,7 @@ int nerf_create(const nerf_config *cfg, int device, nerf_ctx **out) {
     if (is_tc(cfg->mlp_impl)) {
         std::string e;
         const int64_t max_tiles = ((int64_t)c->chunk * c->S + NERF_TILE_M - 1) / NERF_TILE_M;
-        c->tc = tc_create(c->g, max_tiles, c->num_sms, cfg->mlp_impl == NERF_MLP_TCGEN05_SS ? 2 : 0, e);
+        c->tc = tc_create(c->g, max_tiles, c->num_sms, cfg->mlp_impl == NERF_MLP_TCGEN05_SS ? 2 : 0, e, cfg->deterministic_grads != 0);
         if (!c->tc) return bail(NERF_ERR_UNSUPPORTED, e);
     } else {
         const int64_t bc = (int64_t)c->chunk * c->S;

@@ -9,6 +9,7 @@
 //              fitted cost is equal across the 148 CTAs; the sigma row of fc8 is a CUDA-core GEMV
 //              inside the fc8 feature unit, fed by a d(sigma) loader warp.
 // k_pack       gathers the flat f32 [out,in] parameter blob into the bf16 chunk streams.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,6 +43,7 @@ struct WgradArgs {
     const uint8_t *grad_base;
     int32_t act_slots, grad_slots;
     float *grads;
+    float *partials;   // deterministic mode: per-segment partial blocks (WgradWork::part_off), reduced by k_wgrad_reduce; else NULL
 };
 
 // per-CTA wall-clock marks of the last k_wgrad launch (ns, %globaltimer): start, first stage landed, all MMAs done, end
@@ -281,12 +283,18 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
                 }
             }
             ptx::named_bar_sync(1, kEpiThreads);
-            if (has_bias) {
-                for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
-            }
-            if (has_sg) {
-                for (int m = tid; m < u.m_valid; m += kEpiThreads) atomicAdd(a.grads + u.sg_w_base + m, s_sg[m]);
-                if (tid == 0 && u.sg_b_base >= 0) atomicAdd(a.grads + u.sg_b_base, s_sg[256]);
+            if (a.partials) {   // deterministic: the segment's own slots, summed in segment order by k_wgrad_reduce
+                float *pb = a.partials + wk.part_off[seg] + (int64_t)(128 * mblocks) * N;
+                for (int n = tid; n < 256; n += kEpiThreads) pb[n] = has_bias ? s_bias[n] : 0.f;
+                for (int m = tid; m < 260; m += kEpiThreads) pb[256 + m] = has_sg ? s_sg[m] : 0.f;
+            } else {
+                if (has_bias) {
+                    for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
+                }
+                if (has_sg) {
+                    for (int m = tid; m < u.m_valid; m += kEpiThreads) atomicAdd(a.grads + u.sg_w_base + m, s_sg[m]);
+                    if (tid == 0 && u.sg_b_base >= 0) atomicAdd(a.grads + u.sg_b_base, s_sg[256]);
+                }
             }
           } else {
             // (row-major 128B-swizzled panel images, written by the wide-mode chain kernel's bulk stores)
@@ -349,22 +357,40 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
                 if (lane == 0) ptx::mbar_arrive(bars + 8 * (kWgStages + stage));
                 if (++stage == kWgStages) { stage = 0; phase ^= 1u; }
             }
+            // the row groups add their partial sums one after the other (a fixed order: a segment's bias / sigma-row sums are
+            // reproducible; once per segment, so the few extra barriers cost nothing)
             if (has_bias) {
+                for (int g = 0; g < n_rg; ++g) {
+                    if (rg == g) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) atomicAdd(&s_bias[c8 * 8 + e], bsum[e]);
-            }
-            if (sg_active) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) atomicAdd(&s_sg[pc8 * 8 + e], ssum[e]);
-                if (pc8 == 0) atomicAdd(&s_sg[256], dsum);
-            }
-            ptx::named_bar_sync(1, kEpiThreads);
-            if (has_bias) {
-                for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
+                        for (int e = 0; e < 8; ++e) s_bias[c8 * 8 + e] += bsum[e];
+                    }
+                    ptx::named_bar_sync(1, kEpiThreads);
+                }
             }
             if (has_sg) {
-                for (int m = tid; m < u.m_valid; m += kEpiThreads) atomicAdd(a.grads + u.sg_w_base + m, s_sg[m]);
-                if (tid == 0 && u.sg_b_base >= 0) atomicAdd(a.grads + u.sg_b_base, s_sg[256]);
+                for (int g = 0; g < n_prg; ++g) {
+                    if (prg == g) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) s_sg[pc8 * 8 + e] += ssum[e];
+                        if (pc8 == 0) s_sg[256] += dsum;
+                    }
+                    ptx::named_bar_sync(1, kEpiThreads);
+                }
+            }
+            ptx::named_bar_sync(1, kEpiThreads);
+            if (a.partials) {   // deterministic: the segment's own slots, summed in segment order by k_wgrad_reduce
+                float *pb = a.partials + wk.part_off[seg] + (int64_t)(128 * mblocks) * N;
+                for (int n = tid; n < 256; n += kEpiThreads) pb[n] = has_bias ? s_bias[n] : 0.f;
+                for (int m = tid; m < 260; m += kEpiThreads) pb[256 + m] = has_sg ? s_sg[m] : 0.f;
+            } else {
+                if (has_bias) {
+                    for (int n = tid; n < u.n_valid; n += kEpiThreads) atomicAdd(a.grads + u.b_base + n, s_bias[n]);
+                }
+                if (has_sg) {
+                    for (int m = tid; m < u.m_valid; m += kEpiThreads) atomicAdd(a.grads + u.sg_w_base + m, s_sg[m]);
+                    if (tid == 0 && u.sg_b_base >= 0) atomicAdd(a.grads + u.sg_b_base, s_sg[256]);
+                }
             }
           }
         }
@@ -385,7 +411,11 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
                 uint32_t r[32];
                 ptx::tmem_ld32(tmem_base + ((q * 32u) << 16) + (uint32_t)mb * mb_cols + (uint32_t)g * 32u, r);
                 ptx::tmem_ld_wait();
-                if (m < u.m_valid) {
+                if (a.partials) {   // deterministic: plain stores into the segment's own [n][m] block (lanes = m: coalesced)
+                    float *pw = a.partials + wk.part_off[seg] + m;
+#pragma unroll
+                    for (int jn = 0; jn < 32; ++jn) pw[(int64_t)(g * 32 + jn) * (128 * mblocks)] = __uint_as_float(r[jn]);
+                } else if (m < u.m_valid) {
 #pragma unroll
                     for (int jn = 0; jn < 32; ++jn) {
                         const int n = g * 32 + jn;
@@ -400,6 +430,34 @@ __global__ void __launch_bounds__(256, 1) k_wgrad(const WgradArgs a) {
     }
     if (warp == 2) ptx::tmem_dealloc<512>(tmem_base);
     if (threadIdx.x == 0 && blockIdx.x < 256) g_wgrad_marks[4 * blockIdx.x + 3] = global_ns();
+}
+
+// Deterministic mode: fold the segments' partial blocks into the gradient blob, each unit's segments in ascending tile order
+// (a fixed summation order: bit-identical gradients run to run). One thread per element of a unit's block; the segments'
+// values of one element are 2-13 coalesced loads. grid = (blocks, units).
+__global__ void k_wgrad_reduce(const WgradRedUnit *units, const int64_t *seg_off, const float *__restrict__ partials, float *grads) {
+    pdl_trigger();
+    pdl_wait();
+    const WgradRedUnit u = units[blockIdx.y];
+    const int64_t n_w = (int64_t)u.m_pad * u.n_cols, n_all = n_w + 256 + 260;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_all; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t dst = -1;
+        if (i < n_w) {
+            const int m = (int)(i % u.m_pad), n = (int)(i / u.m_pad);
+            if (m < u.m_valid && n < u.n_valid) dst = u.w_base + (int64_t)n * u.w_row_stride + m;
+        } else if (i < n_w + 256) {
+            const int n = (int)(i - n_w);
+            if (u.b_base >= 0 && n < u.n_valid) dst = u.b_base + n;
+        } else if (u.has_sg) {
+            const int m = (int)(i - n_w - 256);
+            if (m < u.m_valid) dst = u.sg_w_base + m;
+            else if (m == 256 && u.sg_b_base >= 0) dst = u.sg_b_base;
+        }
+        if (dst < 0) continue;
+        float sum = 0.f;
+        for (int k = u.seg_begin; k < u.seg_end; ++k) sum += partials[seg_off[k] + i];
+        grads[dst] += sum;   // (+=: a step that runs in micro-batches accumulates launch after launch, in launch order)
+    }
 }
 
 // ---------------------------------------------------------------------------------- pack
@@ -501,6 +559,12 @@ struct TcState {
     uint64_t bias_version = 1;   // bumped by tc_pack_weights (constant-bank copy of the biases)
     int version = 3;             // 3: TS-mode CTA-pair chain (mlp_tc3.cu, hidden <= 256); 2: SS-mode CTA-pair chain (mlp_tc2.cu)
     bool chunk_major = false;    // layout of the saved panels (see k_wgrad)
+    bool deterministic = false;  // weight gradients through per-segment partial blocks + k_wgrad_reduce (fixed order)
+    float *d_partials = nullptr;
+    size_t partials_floats = 0;
+    WgradRedUnit *d_red_units = nullptr;
+    int64_t *d_seg_off = nullptr;
+    int n_red_units = 0;
     Lane2Program *fwd_train2 = nullptr, *fwd_infer2 = nullptr, *bwd2 = nullptr;
     Ts3Program *fwd_train3 = nullptr, *fwd_infer3 = nullptr, *bwd3 = nullptr;
     std::string err;
@@ -513,8 +577,9 @@ static bool upload_stream(const std::vector<PackChunk> &chunks, uint32_t bytes, 
 }
 
 // version: 0 = best for the geometry (TS mode for hidden <= 256, SS mode above), 2 = SS mode, 3 = TS mode
-TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version, std::string &err) {
+TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version, std::string &err, bool deterministic) {
     TcState *s = new TcState();
+    s->deterministic = deterministic;
     s->g = g;
     s->num_sms = num_sms;
     max_tiles = (max_tiles + 1) & ~(int64_t)1;   // the pair kernels walk 256-sample pair tiles
@@ -581,6 +646,9 @@ void tc_destroy(TcState *s) {
     guard_free(s->d_act);
     guard_free(s->d_grad);
     guard_free(s->d_mask);
+    guard_free(s->d_partials);
+    guard_free(s->d_red_units);
+    guard_free(s->d_seg_off);
     tc2_bias_release(s);
     tc3_bias_release(s);
     tc2_free(s->fwd_train2);
@@ -648,13 +716,59 @@ int tc_forward(TcState *s, const float *points, const float *dirs, int64_t n, in
     return 0;
 }
 
-static void build_work(TcState *s, int64_t n_tiles, cudaStream_t st) {
-    if (s->work_tiles == n_tiles) return;
+static bool build_work(TcState *s, int64_t n_tiles, cudaStream_t st) {
+    if (s->work_tiles == n_tiles) return true;
     std::vector<WgradWork> work;
     tc_wgrad_partition(s->plan.units, s->num_sms, n_tiles, work);
+    if (s->deterministic) {
+        // every segment gets a private partial block; a unit's blocks are listed in ascending tile order for the reduction
+        const int U = (int)s->plan.units.size();
+        std::vector<std::vector<std::pair<int, int64_t>>> per_unit((size_t)U);   // (tile_begin, offset)
+        int64_t off = 0;
+        for (WgradWork &w : work) {
+            for (int k = 0; k < w.n_seg; ++k) {
+                const WgradUnit &u = s->plan.units[w.seg[k].unit];
+                const int64_t m_pad = 128 * ((u.n_p + 1) >> 1), n_cols = 64 * u.n_q;
+                w.part_off[k] = off;
+                per_unit[(size_t)w.seg[k].unit].push_back({w.seg[k].tile_begin, off});
+                off += m_pad * n_cols + 256 + 260;
+                off = (off + 31) & ~(int64_t)31;   // 128-byte aligned blocks
+            }
+        }
+        std::vector<WgradRedUnit> red((size_t)U);
+        std::vector<int64_t> seg_off;
+        for (int i = 0; i < U; ++i) {
+            const WgradUnit &u = s->plan.units[i];
+            std::sort(per_unit[(size_t)i].begin(), per_unit[(size_t)i].end());
+            WgradRedUnit r;
+            memset(&r, 0, sizeof(r));
+            r.w_base = u.w_base; r.b_base = u.b_base; r.sg_w_base = u.sg_w_base; r.sg_b_base = u.sg_b_base;
+            r.w_row_stride = u.w_row_stride; r.m_valid = u.m_valid; r.n_valid = u.n_valid;
+            r.m_pad = 128 * ((u.n_p + 1) >> 1); r.n_cols = 64 * u.n_q;
+            r.has_sg = (u.sg_slot >= 0 && u.n_p <= 4) ? 1 : 0;
+            r.seg_begin = (int)seg_off.size();
+            for (auto &pr : per_unit[(size_t)i]) seg_off.push_back(pr.second);
+            r.seg_end = (int)seg_off.size();
+            red[(size_t)i] = r;
+        }
+        if ((size_t)off > s->partials_floats) {
+            cudaStreamSynchronize(st);
+            guard_free(s->d_partials);
+            s->d_partials = nullptr;
+            if (guard_malloc(&s->d_partials, sizeof(float) * (size_t)off) != cudaSuccess) return false;
+            s->partials_floats = (size_t)off;
+        }
+        guard_free(s->d_red_units);
+        guard_free(s->d_seg_off);
+        s->d_red_units = upload(red);
+        s->d_seg_off = upload(seg_off);
+        s->n_red_units = U;
+        if (!s->d_red_units || !s->d_seg_off) return false;
+    }
     cudaMemcpyAsync(s->d_work, work.data(), sizeof(WgradWork) * work.size(), cudaMemcpyHostToDevice, st);
     cudaStreamSynchronize(st);  // `work` is a host temporary
     s->work_tiles = n_tiles;
+    return true;
 }
 
 int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float *d_rgba, int64_t n, float *grads,
@@ -663,7 +777,7 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
     if (n_tiles == 0) return 0;
     if (n_tiles > s->max_tiles) { s->err = "tc_backward: batch exceeds the saved-activation capacity"; return -1; }
     if ((int)s->plan.units.size() > kWgMaxSeg * s->num_sms) { s->err = "tc_backward: too few SMs for the weight-gradient units"; return -1; }
-    build_work(s, n_tiles, st);
+    if (!build_work(s, n_tiles, st)) { s->err = "tc_backward: could not allocate the partial-gradient blocks"; return -1; }
     if (between) between(user, "mlp_dgrad");
     Chain2Launch l;
     if (!chain_launch(s, 2, l, n, 1, st)) return -1;
@@ -675,8 +789,12 @@ int tc_backward(TcState *s, const float *rgba, const float *d_sigma, const float
     w.act_base = s->d_act; w.grad_base = s->d_grad;
     w.act_slots = s->plan.act_slots; w.grad_slots = s->plan.grad_slots;
     w.grads = grads;
+    w.partials = s->deterministic ? s->d_partials : nullptr;
     if (s->chunk_major) launch_pdl(k_wgrad<true>, dim3(s->num_sms), dim3(256), kWgSmem, st, w);
     else launch_pdl(k_wgrad<false>, dim3(s->num_sms), dim3(256), kWgSmem, st, w);
+    if (s->deterministic)
+        launch_pdl(k_wgrad_reduce, dim3(64, (unsigned)s->n_red_units), dim3(256), 0, st, (const WgradRedUnit *)s->d_red_units,
+                   (const int64_t *)s->d_seg_off, (const float *)s->d_partials, grads);
     if (between) between(user, nullptr);
     return 0;
 }

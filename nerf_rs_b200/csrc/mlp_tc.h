@@ -98,6 +98,15 @@ struct WgradUnit {
 struct WgradWork {          // one CTA's assignment: up to kWgMaxSeg (unit, tile range) segments, processed in order
     int32_t n_seg;
     struct { int32_t unit, tile_begin, tile_end; } seg[kWgMaxSeg];
+    // deterministic mode: float offset of the segment's private partial block in the scratch buffer (else unused):
+    // [n][m] dW^T block of 128*mblocks x N floats, then 256 bias sums, then 256 + 4 sigma-row sums
+    int64_t part_off[kWgMaxSeg];
+};
+struct WgradRedUnit {       // deterministic mode: how k_wgrad_reduce folds a unit's partial blocks into the gradient blob
+    int64_t w_base, b_base, sg_w_base, sg_b_base;
+    int32_t w_row_stride, m_valid, n_valid, m_pad, n_cols;
+    int32_t seg_begin, seg_end;      // range in the offset list, in ascending tile order
+    int32_t has_sg;
 };
 
 struct PackChunk {
@@ -244,7 +253,7 @@ int tc3_debug_trace(unsigned long long *out, int n);
 bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err);
 
 struct TcState;
-TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version, std::string &err);
+TcState *tc_create(const NetGeom &g, int64_t max_tiles, int num_sms, int version, std::string &err, bool deterministic = false);
 void tc_destroy(TcState *s);
 size_t tc_bytes_per_tile(const TcState *s);
 void tc_pack_weights(TcState *s, const float *params, cudaStream_t st);

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported_and_bound():
 
 def test_config_struct_matches_header():
     cfg = nb.default_config()
-    assert cfg.struct_size == ctypes.sizeof(nb.NerfConfig) == 18 * 4
+    assert cfg.struct_size == ctypes.sizeof(nb.NerfConfig) == 19 * 4 and cfg.deterministic_grads == 0
     assert (cfg.image_w, cfg.num_rays, cfg.num_samples, cfg.hidden, cfg.xyz_freqs, cfg.dir_freqs, cfg.skip_layer) == (800, 4096, 64, 256, 10, 4, 5)
     assert abs(cfg.learning_rate - 5e-4) < 1e-9          # cli.rs:64-65
     s = nb.as_shipped_config()

@@ -196,3 +196,33 @@ def test_step_is_reproducible():
     scale = np.abs(g0).max()
     for g in grads[1:]:
         assert np.abs(g - g0).max() <= 2e-5 * scale
+
+
+@pytest.mark.parametrize("name", ["ns256_big", "ns512_big"])
+def test_step_is_bit_reproducible_with_deterministic_grads(name):
+    """nerf_config.deterministic_grads = 1: the weight-gradient segments write private partial blocks that one pass reduces in
+    a fixed order (no fp32 atomics) -- gradients, and therefore the Adam update, are bit-identical run to run, and equal to the
+    default (atomic) path up to summation order."""
+    kw = dict(CASES[name])
+    cfg = nb.default_config(image_w=100, image_h=100, deterministic_grads=1, **kw)
+    m = nb.NeRF(cfg)
+    mcfg = G.model_cfg(cfg)
+    w0 = M.flatten_params(M.init_params(mcfg, 0)).numpy()
+    pts, t, dirs, gold = G.make_points(cfg.num_rays, cfg.num_samples, 1)
+    grads, weights = [], []
+    for rep in range(10):
+        m.set_weights(w0)
+        m.set_adam_state(np.zeros_like(w0), np.zeros_like(w0), 0)
+        out, _ = m.predict(pts, t, dirs.reshape(-1), train=True)
+        nb.Trainer(m, 5e-4).step(out, gold)
+        grads.append(m.get_grads())
+        weights.append(m.get_weights())
+    for g, w in zip(grads[1:], weights[1:]):
+        assert np.array_equal(g, grads[0]) and np.array_equal(w, weights[0])
+    # the same gradient as the atomic path, up to fp32 summation order
+    m2 = nb.NeRF(nb.default_config(image_w=100, image_h=100, **kw))
+    m2.set_weights(w0)
+    out, _ = m2.predict(pts, t, dirs.reshape(-1), train=True)
+    nb.Trainer(m2, 5e-4).step(out, gold)
+    g2 = m2.get_grads()
+    assert np.abs(g2 - grads[0]).max() <= 2e-5 * np.abs(g2).max()
