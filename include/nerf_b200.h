@@ -63,7 +63,7 @@ typedef struct nerf_config {
     int32_t image_w, image_h;     /* WIDTH, HEIGHT (ray_sampling.rs:7-8) */
     int32_t num_rays;             /* NUM_RAYS  (model.rs:7)  R */
     int32_t num_samples;          /* NUM_POINTS (model.rs:8) S, <= 256 */
-    int32_t hidden;               /* HIDDEN_NODES (model.rs:12) W: <= 256, or 449..512 (tcgen05 pair kernel; 8 panels) */
+    int32_t hidden;               /* HIDDEN_NODES (model.rs:12) W <= 512; the tensor-core kernels pad it to 64, 128, 256 or 512 */
     int32_t xyz_freqs;            /* positional-encoding octaves for xyz; 0 = raw xyz (INDIM=3, model.rs:11) */
     int32_t dir_freqs;            /* octaves for the view direction; -1 = no direction input (as shipped) */
     int32_t skip_layer;           /* concat [x_enc, h] after this layer's ReLU (5); 0 = none (as shipped) */

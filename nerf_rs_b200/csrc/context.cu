@@ -180,7 +180,9 @@ int check_launch(nerf_ctx *c, const char *what) {
 void build_geom(const nerf_config &cfg, NetGeom &g) {
     memset(&g, 0, sizeof(g));
     g.W = cfg.hidden;
-    g.Wp = (cfg.hidden + 63) / 64 * 64;
+    // the tcgen05 kernels run 1, 2, 4 or 8 hidden panels of 64: every other width is zero-padded up to the next of those
+    // (HIDDEN_NODES is a free constant in the reference, model.rs:12; padding costs tensor work, not correctness)
+    g.Wp = cfg.hidden <= 64 ? 64 : (cfg.hidden <= 128 ? 128 : (cfg.hidden <= 256 ? 256 : (cfg.hidden <= 512 ? 512 : (cfg.hidden + 63) / 64 * 64)));
     g.W2 = cfg.hidden / 2;
     g.W2p = (g.W2 + 63) / 64 * 64;
     g.xyz_freqs = cfg.xyz_freqs;

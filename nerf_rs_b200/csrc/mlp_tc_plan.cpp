@@ -227,7 +227,7 @@ bool tc_build_plan(const NetGeom &g, TcPlan &plan, std::string &err) {
     const int npanels = g.Wp / 64;
     if (g.Wp % 64 || (npanels != 1 && npanels != 2 && npanels != 4 && npanels != 8) || g.W2p % 64 || g.W2p < 64 || g.W2p > 256 ||
         g.Cx > 64 || g.Cd > 32) {
-        err = "tcgen05 MLP supports hidden <= 64, <= 128, 129..256 or 449..512, xyz_freqs <= 10, dir_freqs <= 4";
+        err = "tcgen05 MLP supports hidden <= 512 (padded to 64, 128, 256 or 512), xyz_freqs <= 10, dir_freqs <= 4";
         return false;
     }
     if (g.skip_layer && (g.skip_layer < 1 || g.skip_layer > 6)) {

@@ -20,6 +20,8 @@ CASES = {
     "ns256_big": dict(hidden=256, num_rays=1024, num_samples=64),   # config 0: 512 tiles, > 1 tile per SM
     "ns512": dict(hidden=512, num_rays=10, num_samples=64),         # BASELINE configs[4] width: 8 panels, single-lane pair kernel, 5 tiles
     "ns512_big": dict(hidden=512, num_rays=512, num_samples=128),   # 512 tiles
+    "ns150": dict(hidden=150, num_rays=12, num_samples=64),         # HIDDEN_NODES is a free constant (model.rs:12): padded to 4 panels
+    "ns300": dict(hidden=300, num_rays=12, num_samples=64),         # 257..448: padded to 8 panels (SS-mode pair kernel)
 }
 
 
@@ -84,7 +86,7 @@ def _layer_slices(mcfg):
 @pytest.mark.parametrize("name,impl", [("ns64", _lib.MLP_SIMT_FP32), ("ns256", _lib.MLP_SIMT), ("ns64", _lib.MLP_TCGEN05),
                                        ("ns128", _lib.MLP_TCGEN05), ("ns256", _lib.MLP_TCGEN05),
                                        ("as_shipped", _lib.MLP_TCGEN05), ("ns256_big", _lib.MLP_TCGEN05),
-                                           ("ns512", _lib.MLP_TCGEN05)])
+                                       ("ns512", _lib.MLP_TCGEN05), ("ns150", _lib.MLP_TCGEN05), ("ns300", _lib.MLP_TCGEN05)])
 def test_step_gradients_loss_and_adam(name, impl):
     m, cfg, mcfg, params_t, pts, t, dirs, gold = _setup(name, impl)
     r, s = cfg.num_rays, cfg.num_samples

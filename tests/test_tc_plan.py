@@ -23,6 +23,7 @@ CONFIGS = {
     "w100_as_shipped": dict(hidden=100, xyz_freqs=0, dir_freqs=-1, skip_layer=0, use_rgb_head=0),
     "ns256_noskip_nodir": dict(hidden=256, skip_layer=0, dir_freqs=-1),
     "ns200": dict(hidden=200, xyz_freqs=6, dir_freqs=2, skip_layer=3),
+    "ns150": dict(hidden=150),                                   # 129..192: padded to 4 panels
 }
 
 
@@ -33,7 +34,7 @@ def _mcfg(over):
                          use_rgb_head=bool(d["use_rgb_head"]))
 
 
-WIDE = {"ns512": dict(hidden=512), "ns480_noskip": dict(hidden=480, skip_layer=0)}   # pair kernel only (8 hidden panels)
+WIDE = {"ns512": dict(hidden=512), "ns480_noskip": dict(hidden=480, skip_layer=0), "ns300": dict(hidden=300)}   # (257..448: padded to 8 panels)   # pair kernel only (8 hidden panels)
 
 
 @pytest.mark.parametrize("name", list(CONFIGS) + list(WIDE))
@@ -99,7 +100,7 @@ def test_chunk_stream_is_contiguous_and_bounded():
 
 
 def test_unsupported_geometry_is_rejected():
-    for hidden in (300, 576):      # 5 and 9 panels: neither the 4-panel nor the 8-panel layout
+    for hidden in (576, 1024):     # more than 8 panels (widths up to 512 are padded to 1, 2, 4 or 8 panels)
         cfg = nb.default_config(hidden=hidden)
         with pytest.raises(nb.NerfError):
             U.get_plan(cfg, 0)
