@@ -112,7 +112,7 @@ int comm_p2p_setup(CommState &cs, float *grads0, float *grads1, cudaStream_t st,
     if (!cs.comm || cs.nranks < 2 || cs.nranks > 8) return 0;
     struct Rec { cudaIpcMemHandle_t g0, g1, fl; };
     unsigned int *flags = nullptr;
-    if (cudaMalloc(&flags, 8 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(flags, 0, 8 * sizeof(unsigned int)) != cudaSuccess) {
+    if (cudaMalloc(&flags, 32 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(flags, 0, 32 * sizeof(unsigned int)) != cudaSuccess) {   // [0,8) hand-shake 1, [8,16) hand-shake 2, [16] block counter
         snprintf(err, errlen, "p2p: flag allocation failed");
         return -1;
     }

@@ -462,6 +462,8 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
                 pa.peer_flags[r] = c->comm.peer_flags[r];
             }
             pa.my_flags = c->comm.my_flags;
+            pa.block_counter = c->comm.my_flags + 2 * NERF_MAX_RANKS;
+            pa.n_pad = (c->g.n_params + 3) / 4 * 4;
             pa.rank = c->comm.rank;
             pa.nranks = nranks;
             pa.step = pstep;
@@ -1004,6 +1006,12 @@ int nerf_sync(nerf_ctx *c) {
     if (!c) return NERF_ERR_INVALID_ARG;
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->comm.p2p) {
+        // the fused all-reduce + Adam kernel gives up on a peer that never publishes its gradient (instead of trapping or
+        // hanging): from then on the replicas have diverged, which the host must hear about
+        const unsigned int ts = adam_p2p_timeout_step();
+        if (ts) return fail(c, NERF_ERR_COMM, "peer gradient exchange timed out at step " + std::to_string(ts) + ": the replicas have diverged");
+    }
     return check_launch(c, "sync");
 }
 
@@ -1174,7 +1182,7 @@ int nerf_comm_init_rank(nerf_ctx *c, const void *id128, int32_t rank, int32_t nr
     // peer-memory gradient exchange (fused all-reduce + Adam); NERF_B200_P2P=0 keeps the plain NCCL all-reduce
     const char *env = getenv("NERF_B200_P2P");
     if (nranks > 1 && nranks <= NERF_MAX_RANKS && !(env && env[0] == '0')) {
-        const size_t bytes = sizeof(float) * ((c->g.n_params + 3) / 4 * 4);
+        const size_t bytes = 2 * sizeof(float) * ((c->g.n_params + 3) / 4 * 4);   // local gradient | reduced gradient (kernels.h)
         for (int b = 0; b < 2; ++b) {
             if (!c->d_gacc[b]) CU(c, cudaMalloc(&c->d_gacc[b], bytes));   // (plain: the IPC export needs the allocation base)
             CU(c, cudaMemsetAsync(c->d_gacc[b], 0, bytes, c->stream));

@@ -86,21 +86,27 @@ struct AdamArgs {
 };
 void launch_adam(const AdamArgs &a, int num_sms, cudaStream_t st);
 
-// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel training, one process per GPU).
-// Every rank reads all ranks' local gradient buffers directly (peer pointers opened with CUDA IPC), sums them in
-// rank order -- so every replica applies bit-identical updates -- and runs Adam on its own copy of the parameters.
-// Cross-GPU hand-shake: monotonic step counters in each rank's flag array (flags[r] = last step for which rank r's
-// gradient is complete), written remotely with system-scope release stores and polled locally.
+// Fused gradient all-reduce + Adam over NVLink peer memory (data-parallel training, one process per GPU), in ONE kernel:
+//   hand-shake 1  every rank's local gradient for this step is complete (flags[r] = step, system-scope release stores)
+//   reduce-scatter rank r sums shard r of all ranks' gradient buffers (peer loads, fixed rank order) into the "reduced" half
+//                  of its own buffer
+//   hand-shake 2  (flags[8 + r] = step) every rank's reduced shard is in place
+//   all-gather + Adam  every rank reads the N reduced shards (N - 1 of them over NVLink) and updates its replica
+// Per rank 2 (N-1)/N gradient sizes cross NVLink instead of N - 1 (one-shot pull), every element is summed once, in rank
+// order, by one rank -- all replicas apply bit-identical updates. Buffers: [0, n_pad) local gradient, [n_pad, 2 n_pad) reduced.
 #define NERF_MAX_RANKS 8
 struct AdamP2PArgs {
     AdamArgs adam;                        // adam.g = where the summed gradient is written back (nerf_get_grads)
-    const float *peer_grads[NERF_MAX_RANKS];   // rank r's local gradient buffer for this step (index == rank)
-    unsigned int *peer_flags[NERF_MAX_RANKS];  // rank r's flag array [NERF_MAX_RANKS]
+    float *peer_grads[NERF_MAX_RANKS];    // rank r's gradient buffer pair (local | reduced) for this step (index == rank)
+    unsigned int *peer_flags[NERF_MAX_RANKS];  // rank r's flag array [2 * NERF_MAX_RANKS]
     unsigned int *my_flags;
+    unsigned int *block_counter;          // zero-initialised; the last block of phase 1 publishes hand-shake 2 and resets it
+    int64_t n_pad;                        // floats between the local and the reduced half
     int32_t rank, nranks;
     uint32_t step;                        // > 0, monotonic
 };
 void launch_adam_p2p(const AdamP2PArgs &a, int num_sms, cudaStream_t st);
+unsigned int adam_p2p_timeout_step();
 void launch_init_uniform(float *p, const NetGeom &g, uint64_t seed, cudaStream_t st);
 
 // ---------------------------------------------------------------- mlp_simt.cu
