@@ -699,8 +699,6 @@ Ts3Program *tc3_upload(const TsProgram &p, std::string &err) {
     }
     Ts3Program *d = new Ts3Program();
     d->prog = p;
-    if (getenv("NERF_TC3_NOMASK"))   // timing experiment only (wrong gradients): the backward chain without its ReLU-mask loads
-        for (auto &st : d->prog.steps) if (st.kind == EK_DMASK) st.kind = EK_DCOPY;
     return d;
 }
 void tc3_free(Ts3Program *d) { delete d; }
