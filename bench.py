@@ -76,21 +76,37 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.active = True            # rows are recorded only while set (the caller clears it around untimed work)
+        self.ready = threading.Event()  # NVML initialised (or the nvidia-smi fallback chosen): sampling has begun
+        self._query = None
 
     def run(self):
         if self._run_nvml():
             return
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+        def query():
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            return [x.strip() for x in out.split(",")] if out else None
+        self._query = query
+        self.ready.set()
         while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
+            self.sample_now()
             time.sleep(0.1)
+
+    def sample_now(self):
+        """One sample, from whichever thread calls it (the timing loop takes one right after enqueueing its steps, so that even a
+        30 ms window holds a sample taken under load)."""
+        if not self.active or self._query is None:
+            return
+        try:
+            row = self._query()
+            if row:
+                self.rows.append(row)
+        except Exception:
+            pass
 
     def _run_nvml(self):
         """Same fields through NVML (a query costs ~0.1 ms instead of nvidia-smi's ~0.5 s): one sample every 20 ms."""
@@ -105,14 +121,16 @@ class ClockSampler(threading.Thread):
             get_reasons(h)
         except Exception:
             return False
+
+        def query():
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            r = get_reasons(h)
+            return [str(sm), str(mx)] + [("Active" if r & b else "Not Active") for _, b in bits]
+        self._query = query
+        self.ready.set()
         while not self.stop_flag:
-            try:
-                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
-                r = get_reasons(h)
-                self.rows.append([str(sm), str(mx)] + [("Active" if r & b else "Not Active") for _, b in bits])
-            except Exception:
-                pass
-            time.sleep(0.02)
+            self.sample_now()
+            time.sleep(0.005)
         return True
 
     def summary(self):
@@ -252,15 +270,20 @@ class Harness:
         return float(t.item())
 
 
-def train_throughput(h, model, rays, steps, warmup, seed0=1000):
-    """`steps` device-resident training iterations between barriers, CUDA events on the library's stream, max over ranks."""
+def train_throughput(h, model, rays, steps, warmup, seed0=1000, sampler=None):
+    """`steps` device-resident training iterations between barriers, CUDA events on the library's stream, max over ranks.
+    `sampler` (a ClockSampler) records clocks from the first timed launch on, warm-up excluded."""
     for it in range(warmup):
         model.train_iter(1 + it)
     h.barrier(model)
     l0 = model.launch_count
+    if sampler is not None:
+        sampler.active = True
     model.timer_start()
     for it in range(steps):
         model.train_iter(seed0 + it)
+    if sampler is not None:
+        sampler.sample_now()          # the launches are queued, the GPU is inside the timed steps
     ms = model.timer_stop()
     launches = model.launch_count - l0
     h.barrier(model)
@@ -363,8 +386,10 @@ def main():
 
     # ---- headline: EXACTLY --steps device-resident iterations
     sampler = ClockSampler(local)
+    sampler.active = False
     sampler.start()
-    value, ms_step, launches = train_throughput(h, model, rays, args.steps, args.warmup)
+    sampler.ready.wait(10.0)
+    value, ms_step, launches = train_throughput(h, model, rays, args.steps, args.warmup, sampler=sampler)
     window_s = ms_step * args.steps * 1e-3
     loss = model.last_loss()
 
@@ -378,6 +403,7 @@ def main():
         blocks = []
         sampler2 = ClockSampler(local)
         sampler2.start()
+        sampler2.ready.wait(10.0)
         t_begin = time.perf_counter()
         while h.max_over_ranks(time.perf_counter() - t_begin) < 2.0 and len(blocks) < 200:   # (the same decision on every rank)
             _, b_ms, _ = train_throughput(h, model, rays, args.steps, 0, seed0=20000 + 1000 * len(blocks))
@@ -499,6 +525,10 @@ def main():
                                               image_w=IMG, image_h=IMG, num_rays=65536 // world, num_samples=128, hidden=512),
         }
 
+    if world > 1:                      # the multi-GPU part is over: leave the communicator together, the rest is rank 0's
+        h.barrier(model)
+        model.comm_destroy()
+        h.dist.destroy_process_group()
     if rank != 0:
         return
     # ---- the HBM-bound stage kernels alone at render-scale sizes (working set > L2): sampling, compositing fwd/bwd, Adam

@@ -304,6 +304,10 @@ class NeRF:
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(uid)
         _check(self.h, self.lib.nerf_comm_init_rank(self.h, buf, rank, nranks))
 
+    def comm_destroy(self):
+        """Leave the communicator (collective: every rank calls it; peers wait for each other's last exchange to finish)."""
+        _check(self.h, self.lib.nerf_comm_destroy(self.h))
+
     # ---- measurement
     def timer_start(self):
         _check(self.h, self.lib.nerf_timer_start(self.h))

@@ -272,9 +272,10 @@ void launch_adam_p2p(const AdamP2PArgs &a, int num_sms, cudaStream_t st) {
     // either (the exchange waits for the slowest GPU, not for bytes), so the one-shot kernel -- one hand-shake less -- is used
     // while (N - 1) gradient sizes per rank are a few microseconds of NVLink time, the two-phase kernel beyond that.
     // NERF_B200_P2P=2 / =3 force the one-shot / the two-phase kernel (A/B runs).
-    static const char *env = getenv("NERF_B200_P2P");
+    const char *env = getenv("NERF_B200_P2P");
+    const char sel = env ? env[0] : 0;
     const bool big = (double)a.adam.n * 4.0 * (a.nranks - 1) > 32e6;
-    const bool oneshot = env && env[0] == '2' ? true : (env && env[0] == '3' ? false : !big);
+    const bool oneshot = sel == '2' ? true : (sel == '3' ? false : !big);
     if (oneshot) launch_pdl(k_adam_p2p_oneshot, dim3(blocks), dim3(256), 0, st, a);
     else launch_pdl(k_adam_p2p, dim3(blocks), dim3(256), 0, st, a);
 }

@@ -2,6 +2,8 @@
 // The reference has no multi-device code; this is the one exchange step the
 // data-parallel path needs.
 #include "comm.h"
+#include <chrono>
+#include <thread>
 
 #include <dlfcn.h>
 
@@ -112,7 +114,7 @@ int comm_p2p_setup(CommState &cs, float *grads0, float *grads1, cudaStream_t st,
     if (!cs.comm || cs.nranks < 2 || cs.nranks > 8) return 0;
     struct Rec { cudaIpcMemHandle_t g0, g1, fl; };
     unsigned int *flags = nullptr;
-    if (cudaMalloc(&flags, 32 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(flags, 0, 32 * sizeof(unsigned int)) != cudaSuccess) {   // [0,8) hand-shake 1, [8,16) hand-shake 2, [16] block counter
+    if (cudaMalloc(&flags, 32 * sizeof(unsigned int)) != cudaSuccess || cudaMemset(flags, 0, 32 * sizeof(unsigned int)) != cudaSuccess) {   // [0,8) hand-shake 1, [8,16) hand-shake 2, [16] block counter, [24,32) good-bye (comm_destroy)
         snprintf(err, errlen, "p2p: flag allocation failed");
         return -1;
     }
@@ -178,6 +180,25 @@ int comm_p2p_setup(CommState &cs, float *grads0, float *grads1, cudaStream_t st,
 
 void comm_destroy(CommState &cs) {
     if (cs.my_flags) {
+        // Leave together: a peer may still be inside its last exchange kernel, reading this rank's gradient buffers, when this
+        // rank (whose own stream the caller has synchronised) gets here. Say good-bye in every peer's flag array (slot 24 + rank)
+        // and wait until every peer has said it here -- a peer says it only after ITS stream has drained. A peer that never
+        // calls destroy costs the time-out, not a hang.
+        if (cs.p2p && cs.p2p_step > 0) {
+            const unsigned int bye = 1;
+            for (int r = 0; r < cs.nranks; ++r)
+                if (r != cs.rank && cs.peer_flags[r]) cudaMemcpy(cs.peer_flags[r] + 24 + cs.rank, &bye, sizeof(bye), cudaMemcpyHostToDevice);
+            const auto t0 = std::chrono::steady_clock::now();
+            for (;;) {
+                unsigned int seen[8] = {0};
+                if (cudaMemcpy(seen, cs.my_flags + 24, sizeof(seen), cudaMemcpyDeviceToHost) != cudaSuccess) break;
+                bool all = true;
+                for (int r = 0; r < cs.nranks; ++r) all = all && (r == cs.rank || seen[r] != 0);
+                if (all || std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5)) break;
+                std::this_thread::sleep_for(std::chrono::microseconds(200));
+            }
+            cudaGetLastError();
+        }
         for (int r = 0; r < cs.nranks; ++r) {
             if (r == cs.rank) continue;
             for (int b = 0; b < 2; ++b) if (cs.peer_grads[b][r]) cudaIpcCloseMemHandle(cs.peer_grads[b][r]);

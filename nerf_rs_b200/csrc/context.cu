@@ -1195,6 +1195,8 @@ int nerf_comm_init_rank(nerf_ctx *c, const void *id128, int32_t rank, int32_t nr
 
 int nerf_comm_destroy(nerf_ctx *c) {
     if (!c) return NERF_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);   // comm_destroy's good-bye means "my stream has drained"
     comm_destroy(c->comm);
     return NERF_OK;
 }
