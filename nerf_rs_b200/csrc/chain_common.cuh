@@ -147,6 +147,9 @@ __device__ __forceinline__ void epi_half(const float *cbias, const uint32_t (&r)
     if (kKind == EK_RELU || kKind == EK_LINEAR) {
 #pragma unroll
         for (int j2 = 0; j2 < 8; ++j2) {
+#ifdef NERF_TC3_NOBIAS   // timing experiment (wrong results): what the bias add costs
+            float v0 = __uint_as_float(r[2 * j2]), v1 = __uint_as_float(r[2 * j2 + 1]);
+#else
             const float4 b4 = reinterpret_cast<const float4 *>(cbias)[(bidx >> 2) + 4 * kHalf + (j2 >> 1)];
             const float2 b = (j2 & 1) ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y);
             unsigned long long acc2, bias2, sum2;
@@ -155,6 +158,7 @@ __device__ __forceinline__ void epi_half(const float *cbias, const uint32_t (&r)
             asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sum2) : "l"(acc2), "l"(bias2));
             float v0, v1;
             asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(sum2));
+#endif
             w[j2] = (kKind == EK_RELU) ? ptx::pack_bf16x2_relu(v0, v1) : ptx::pack_bf16x2(v0, v1);
         }
     } else if (kKind == EK_DMASK) {
