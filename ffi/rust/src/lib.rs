@@ -84,6 +84,7 @@ pub mod sys {
         pub fn nerf_predict_points(ctx: *mut nerf_ctx, query_points: *const f32, n_points_floats: i64,
                                    distances: *const f32, n_distances: i64, dirs: *const f32, train: i32,
                                    out_rgba: *mut f32, out_sigma: *mut f32) -> c_int;
+        pub fn nerf_get_predictions(ctx: *mut nerf_ctx, out_rgba: *mut f32, out_sigma: *mut f32) -> c_int;
         pub fn nerf_compositing(ctx: *mut nerf_ctx, densities: *const f32, colors: *const f32, distances: *const f32,
                                 num_rays: i32, num_samples: i32, out: *mut f32) -> c_int;
         pub fn nerf_step(ctx: *mut nerf_ctx, gold: *const f32, n_gold: i64, loss: *mut f32) -> c_int;
@@ -229,6 +230,25 @@ impl NeRF {
         Ok((out, sigma))
     }
 
+    /// The prediction as the reference has it -- a device tensor (main.rs:58): enqueues the forward, no device synchronisation.
+    /// `Trainer::step_device` consumes it; `predictions()` fetches pixels and densities when the host draws (main.rs:86-89).
+    pub fn predict_device(&self, query_points: &[f32], distances: &[f32], dirs: Option<&[f32]>) -> Result<(), NerfError> {
+        check(self.ctx, unsafe {
+            sys::nerf_predict_points(self.ctx, query_points.as_ptr(), query_points.len() as i64, distances.as_ptr(),
+                                     distances.len() as i64, dirs.map_or(std::ptr::null(), |d| d.as_ptr()), 1,
+                                     std::ptr::null_mut(), std::ptr::null_mut())
+        })
+    }
+    /// (colors [R*4], densities [R*S]) of the current batch from the device.
+    pub fn predictions(&self) -> Result<(Vec<f32>, Vec<f32>), NerfError> {
+        let r = self.cfg.num_rays as usize;
+        let s = self.cfg.num_samples as usize;
+        let mut out = vec![0f32; r * 4];
+        let mut sigma = vec![0f32; r * s];
+        check(self.ctx, unsafe { sys::nerf_get_predictions(self.ctx, out.as_mut_ptr(), sigma.as_mut_ptr()) })?;
+        Ok((out, sigma))
+    }
+
     /// `NeRF::save` / `NeRF::load` (model.rs:211-217) as flat f32 blobs.
     pub fn weights(&self) -> Result<Vec<f32>, NerfError> {
         let n = unsafe { sys::nerf_num_params(self.ctx) };
@@ -269,6 +289,12 @@ impl Trainer {
         Trainer
     }
 
+    /// `Trainer::step` on the device-resident prediction of `NeRF::predict_device`.
+    pub fn step_device(&mut self, model: &mut NeRF, gold: &[f32], _iter: &usize) -> Result<f32, NerfError> {
+        let mut loss = 0f32;
+        check(model.raw(), unsafe { sys::nerf_step(model.raw(), gold.as_ptr(), gold.len() as i64, &mut loss) })?;
+        Ok(loss)
+    }
     /// `Trainer::step(&predictions [R,4], gold [R*4], &iter) -> f32` (model.rs:311).
     pub fn step(&mut self, model: &mut NeRF, predictions: &[f32], gold: &[f32], _iter: &usize) -> Result<f32, NerfError> {
         if predictions.len() != model.cfg.num_rays as usize * 4 {

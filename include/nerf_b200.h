@@ -144,6 +144,16 @@ int nerf_get_batch(nerf_ctx *ctx, const int64_t *indices_yx, const int64_t *view
 int nerf_predict(nerf_ctx *ctx, int32_t train, float *out_rgba, float *out_sigma);
 int nerf_predict_points(nerf_ctx *ctx, const float *query_points, int64_t n_points_floats, const float *distances,
                         int64_t n_distances, const float *dirs, int32_t train, float *out_rgba, float *out_sigma);
+/* The reference's predict returns a device Tensor that Trainer::step consumes (main.rs:58 -> :72) and the host reads only when
+ * it draws (draw_predictions every eval_steps, main.rs:86-89). The same here: with BOTH outputs NULL nerf_predict* enqueues the
+ * forward and returns without a device synchronisation, and nerf_get_predictions copies the current batch's pixels [R*4] and /
+ * or densities [R*S] to the host whenever the caller wants them -- after predict, or after nerf_step / nerf_train_iter on that
+ * batch (NERF_ERR_STATE if the context holds no prediction).
+ * Host buffers handed to a call that returns without synchronising (nerf_predict_points with NULL outputs) follow the rule of
+ * cudaMemcpyAsync: pageable memory (a Rust Vec, a numpy array) has been staged when the call returns; PINNED memory must stay
+ * unchanged until the next call that returns a value from the device (nerf_step with a loss pointer, nerf_get_predictions,
+ * nerf_sync). */
+int nerf_get_predictions(nerf_ctx *ctx, float *out_rgba, float *out_sigma);
 
 /* ---- compositing (src/model.rs:234-249), standalone on caller buffers ---------------
  * densities [R][S], colors [R][S][4], distances [R][S] = deltas between adjacent
@@ -154,7 +164,10 @@ int nerf_compositing(nerf_ctx *ctx, const float *densities, const float *colors,
 /* ---- Trainer::step (src/model.rs:311-325) -------------------------------------------
  * gold [R*4] host RGBA, or NULL to use the gold gathered by nerf_get_batch.
  * Runs MSE (model.rs:296-299) + backward + Adam. loss may be NULL (no host sync);
- * otherwise the call blocks for the scalar like f32::try_from(&loss) (model.rs:324).
+ * otherwise the call blocks for the scalar like f32::try_from(&loss) (model.rs:324) -- for the SCALAR, not for the step: the
+ * loss is final after the compositing backward, and the call returns while dgrad, weight gradients and Adam are still running
+ * (every later call is ordered behind them on the context's stream; nerf_sync waits for everything). A nerf_predict_points that
+ * follows directly copies its inputs to the device under the rest of this step.
  * With a communicator the loss (here and in nerf_last_loss) is the RANK-LOCAL mean over this rank's R*4 elements;
  * the global-batch loss is the mean of the ranks' values. */
 int nerf_step(nerf_ctx *ctx, const float *gold, int64_t n_gold, float *loss);

@@ -6,5 +6,5 @@ surface used by the tests and ``bench.py``. Importing it never touches the oracl
 no CPU fallback: without the built library or a B200 the constructors raise.
 """
 from ._lib import NerfConfig, NerfError, load, LIB_PATH  # noqa: F401
-from .api import (NeRF, Trainer, compositing, get_multiview_batch, get_view_angles, default_config,  # noqa: F401
+from .api import (NeRF, Trainer, Prediction, compositing, get_multiview_batch, get_view_angles, default_config,  # noqa: F401
                   as_shipped_config, load_image_as_array, load_image_rgba8, get_image_paths)

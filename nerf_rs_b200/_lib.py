@@ -70,6 +70,7 @@ SIGNATURES = {
     "nerf_get_batch": (ctypes.c_int, [vp, vp, vp, i32, vp, i32, u64, vp, vp, vp, vp, vp]),
     "nerf_predict": (ctypes.c_int, [vp, i32, vp, vp]),
     "nerf_predict_points": (ctypes.c_int, [vp, vp, i64, vp, i64, vp, i32, vp, vp]),
+    "nerf_get_predictions": (ctypes.c_int, [vp, vp, vp]),
     "nerf_compositing": (ctypes.c_int, [vp, vp, vp, vp, i32, i32, vp]),
     "nerf_step": (ctypes.c_int, [vp, vp, i64, P(f32)]),
     "nerf_train_iter": (ctypes.c_int, [vp, u64]),

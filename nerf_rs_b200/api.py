@@ -203,6 +203,7 @@ class NeRF:
         """dataset::get_multiview_batch body (dataset.rs:72-138) with caller-supplied or Philox randomness.
         Returns a dict of the requested host arrays; the batch also stays resident for predict()."""
         r, s = self.num_rays, self.num_points
+        self._pred_gen = getattr(self, "_pred_gen", 0) + 1   # (a new batch invalidates Prediction handles)
         idx = None if indices is None else np.ascontiguousarray(indices, dtype=np.int64).reshape(r, 2)
         vi = None if view_index is None else np.ascontiguousarray(view_index, dtype=np.int64)
         if n_picks is None:
@@ -224,14 +225,18 @@ class NeRF:
                                               _ptr(out.get("dirs")), _ptr(out.get("indices"))))
         return out
 
-    def predict(self, query_points=None, distances=None, dirs=None, train=True, want_sigma=True):
+    def predict(self, query_points=None, distances=None, dirs=None, train=True, want_sigma=True, lazy=False):
         """NeRF::predict (model.rs:152-209): (pixels [R,4], densities [R,S]).
 
         With arrays: the literal signature -- flat query_points [B*3], distances [B] (t values),
-        dirs [R*3] if the config has a direction input. Without: runs on the resident batch."""
+        dirs [R*3] if the config has a direction input. Without: runs on the resident batch.
+        lazy=True: the prediction stays on the device, like the Tensor the reference's predict returns (main.rs:58): the
+        call enqueues the forward and returns (Prediction, None) without a device synchronisation; Trainer.step takes the
+        handle, `.numpy()` / `.densities()` fetch the values when the host wants them (draw_predictions, main.rs:86-89)."""
         r, s = self.num_rays, self.num_points
-        out = np.empty((r, 4), dtype=np.float32)
-        sig = np.empty((r, s), dtype=np.float32) if want_sigma else None
+        self._pred_gen = getattr(self, "_pred_gen", 0) + 1
+        out = None if lazy else np.empty((r, 4), dtype=np.float32)
+        sig = np.empty((r, s), dtype=np.float32) if (want_sigma and not lazy) else None
         if query_points is None:
             _check(self.h, self.lib.nerf_predict(self.h, 1 if train else 0, _ptr(out), _ptr(sig)))
         else:
@@ -240,6 +245,15 @@ class NeRF:
                 raise NerfError(_lib.ERR_INVALID_ARG, "predict expects 1-D tensors (model.rs:162-163)")
             _check(self.h, self.lib.nerf_predict_points(self.h, _ptr(qp), qp.size, _ptr(di), di.size, _ptr(dr), 1 if train else 0,
                                                         _ptr(out), _ptr(sig)))
+        if lazy:
+            return Prediction(self), None
+        return out, sig
+
+    def get_predictions(self, want_pixels=True, want_sigma=False):
+        """Pixels [R,4] and / or densities [R,S] of the current batch from the device (nerf_get_predictions)."""
+        out = np.empty((self.num_rays, 4), dtype=np.float32) if want_pixels else None
+        sig = np.empty((self.num_rays, self.num_points), dtype=np.float32) if want_sigma else None
+        _check(self.h, self.lib.nerf_get_predictions(self.h, _ptr(out), _ptr(sig)))
         return out, sig
 
     def render(self, yaw, pitch, y0=0, y1=None, randomize=False, seed=0, packed=False):
@@ -283,6 +297,7 @@ class NeRF:
         return out
 
     def train_iter(self, seed):
+        self._pred_gen = getattr(self, "_pred_gen", 0) + 1
         _check(self.h, self.lib.nerf_train_iter(self.h, seed))
 
     def last_loss(self):
@@ -368,6 +383,34 @@ def compositing(model, densities, colors, distances):
     return out
 
 
+class Prediction:
+    """Device-resident result of NeRF.predict(..., lazy=True): the counterpart of the Tensor the reference's predict returns and
+    Trainer::step consumes (main.rs:58 -> :72). Valid until the model's next predict."""
+
+    def __init__(self, model):
+        self.model = model
+        self.gen = model._pred_gen
+        self.shape = (model.num_rays, 4)
+
+    def _current(self):
+        if self.model.h is None or self.gen != getattr(self.model, "_pred_gen", 0):
+            raise NerfError(_lib.ERR_STATE, "stale prediction handle: the model has run another predict since")
+
+    def numpy(self):
+        """pixels [R,4] on the host"""
+        self._current()
+        return self.model.get_predictions(True, False)[0]
+
+    def densities(self):
+        """densities [R,S] on the host"""
+        self._current()
+        return self.model.get_predictions(False, True)[1]
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+
 class Trainer:
     """Trainer::new / Trainer::step (model.rs:301-325). Adam state lives in the model's context;
     lr is fixed at context creation (cli.rs:64-65), so `lr` here must match the config."""
@@ -382,7 +425,11 @@ class Trainer:
         """predictions: the array predict() returned (kept for signature parity: the tape is in the
         context); gold: flat [R*4] (model.rs:316). Returns the loss as a host float (model.rs:324)."""
         m = self.model
-        if predictions is not None and tuple(np.shape(predictions)) != (m.num_rays, 4):
+        if isinstance(predictions, Prediction):
+            if predictions.model is not m:
+                raise NerfError(_lib.ERR_INVALID_ARG, "the prediction belongs to another model")
+            predictions._current()
+        elif predictions is not None and tuple(np.shape(predictions)) != (m.num_rays, 4):
             raise NerfError(_lib.ERR_INVALID_ARG, "predictions must be [NUM_RAYS, LABELS] (model.rs:315)")
         g = _f32(gold)
         if g is not None and g.ndim != 1:

@@ -142,9 +142,12 @@ struct nerf_ctx {
     uint32_t *d_frame_0rgb = nullptr;
     uint8_t *d_metrics = nullptr;        // scratch of nerf_log_metrics (lazily allocated)
     // nerf_predict_points: the host->device copy of the points overlaps the forward kernel (chunked copy on its own stream)
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host copies that overlap kernels: chunked points (nerf_predict_points), the early loss read (nerf_step)
     cudaEvent_t ev_main = nullptr, ev_dirs = nullptr, ev_all = nullptr;
-    unsigned int *d_h2d_flag = nullptr, *h_h2d_seq = nullptr;   // device counter; pinned 1, 2, 3, ... source values
+    cudaEvent_t ev_cbwd = nullptr;        // recorded after a step's compositing backward: the loss is final, the batch inputs have no reader left
+    bool inputs_free = false;             // the last enqueuing API call was a single-launch nerf_step (ev_cbwd covers every reader of the inputs)
+    int h2d_word = 0;                     // which of the two arrival counters the next overlapped copy uses
+    unsigned int *d_h2d_flag = nullptr, *h_h2d_seq = nullptr;   // two device counters (alternating per call); pinned 1, 2, 3, ... source values
     const unsigned int *h2d_flag_active = nullptr;               // non-NULL while the resident points are still arriving
     int64_t h2d_chunk_samples = 0;
 };
@@ -160,6 +163,14 @@ int fail(nerf_ctx *c, int code, const std::string &msg) {
         cudaError_t e_ = (expr);                                                                      \
         if (e_ != cudaSuccess)                                                                        \
             return fail(c, NERF_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+// Every public entry point that enqueues work starts with ENTER: device selection, and "the previous call was not the step
+// whose compositing-backward event covers all readers of the batch inputs" (nerf_predict_points reads the flag before ENTER).
+#define ENTER(c)                                  \
+    do {                                          \
+        CU(c, cudaSetDevice((c)->device));        \
+        (c)->inputs_free = false;                 \
     } while (0)
 
 struct Scope {
@@ -347,6 +358,9 @@ int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool s
         c->predicted = true;
         return NERF_OK;
     }
+    // Nobody asked for the pixels yet (device-resident prediction): a training forward leaves compositing to nerf_step's
+    // backward kernel, which recomputes the pixels anyway, or to nerf_get_predictions / nerf_log_metrics (ensure_outputs).
+    if (!out_rgba && !out_sigma && train && c->chunk >= c->R) skip_composite = true;
     if (forward_done) {   // (nerf_predict_points already ran the single-launch forward under its overlapped host copy)
         if (train) c->acts_valid = true;
     } else {
@@ -366,6 +380,31 @@ int do_predict(nerf_ctx *c, int train, float *out_rgba, float *out_sigma, bool s
     if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_out, sizeof(float) * 4 * c->R, cudaMemcpyDeviceToHost, c->stream));
     if (out_sigma) CU(c, cudaMemcpyAsync(out_sigma, c->d_sigma, sizeof(float) * c->B, cudaMemcpyDeviceToHost, c->stream));
     if (out_rgba || out_sigma) CU(c, cudaStreamSynchronize(c->stream));
+    return NERF_OK;
+}
+
+int ensure_copy_stream(nerf_ctx *c) {
+    if (c->copy_stream) return NERF_OK;
+    constexpr int kChunks = 8;
+    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&c->ev_all, cudaEventDisableTiming));
+    CU(c, cudaEventCreateWithFlags(&c->ev_cbwd, cudaEventDisableTiming));
+    CU(c, guard_malloc(&c->d_h2d_flag, 2 * sizeof(unsigned int)));
+    CU(c, cudaMemsetAsync(c->d_h2d_flag, 0, 2 * sizeof(unsigned int), c->stream));
+    CU(c, cudaMallocHost(&c->h_h2d_seq, sizeof(unsigned int) * kChunks));
+    for (int k = 0; k < kChunks; ++k) c->h_h2d_seq[k] = (unsigned int)k + 1u;
+    return NERF_OK;
+}
+
+// pixels of the current batch on demand (a prediction whose compositing was deferred)
+int ensure_outputs(nerf_ctx *c) {
+    if (c->outputs_valid) return NERF_OK;
+    if (!c->batch_valid || !c->predicted || c->fwd_deferred) return fail(c, NERF_ERR_STATE, "no prediction on this batch (call nerf_predict first)");
+    int rc = composite_forward(c, c->R, c->d_out);
+    if (rc) return rc;
+    c->outputs_valid = true;
     return NERF_OK;
 }
 
@@ -413,9 +452,16 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     float *gacc = p2p ? c->d_gacc[(c->comm.p2p_step + 1) & 1] : c->d_grads;
     CU(c, cudaMemsetAsync(gacc, 0, sizeof(float) * c->g.n_params, c->stream));   // (before the kernels, so that they stay back to back for the programmatic launches)
     int rc = NERF_OK;
+    bool cbwd_recorded = false;
     if (!c->fwd_deferred) {
         rc = composite_backward(0, c->R);
         if (rc) return rc;
+        if (loss || c->copy_stream) {   // (the fused device-resident iteration with no loss read needs neither)
+            rc = ensure_copy_stream(c);
+            if (rc) return rc;
+            CU(c, cudaEventRecord(c->ev_cbwd, c->stream));
+            cbwd_recorded = true;
+        }
     }
     for (int r0 = 0; r0 < c->R; r0 += c->chunk) {
         const int nr = (c->R - r0 < c->chunk) ? c->R - r0 : c->chunk;
@@ -478,12 +524,24 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     rc = ensure_packed(c);
     if (rc) return rc;
     if (loss) {
-        CU(c, cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
+        // The loss is final once the compositing backward has run -- long before dgrad, wgrad and Adam finish. It is read on the
+        // copy stream behind that kernel's event, so the call returns (like f32::try_from(&loss) on an asynchronous backend,
+        // model.rs:322-324) while the rest of the step is still running and the host can already enqueue the next batch's copies.
+        static const bool sync_step = getenv("NERF_B200_STEP_SYNC") != nullptr;   // A/B: wait for the whole step
+        if (cbwd_recorded && !sync_step) {
+            CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_cbwd, 0));
+            CU(c, cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+            CU(c, cudaStreamSynchronize(c->copy_stream));
+        } else {
+            CU(c, cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+        }
         float l = *c->h_loss;
         *loss = l;
     }
-    return check_launch(c, "step");
+    rc = check_launch(c, "step");
+    c->inputs_free = rc == NERF_OK && cbwd_recorded;
+    return rc;
 }
 
 int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick, const ViewPose *poses, int fixed_view,
@@ -589,7 +647,7 @@ int nerf_destroy(nerf_ctx *c) {
     if (c->copy_stream) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamDestroy(c->copy_stream);
-        cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_dirs); cudaEventDestroy(c->ev_all);
+        cudaEventDestroy(c->ev_main); cudaEventDestroy(c->ev_dirs); cudaEventDestroy(c->ev_all); cudaEventDestroy(c->ev_cbwd);
         guard_free(c->d_h2d_flag);
         cudaFreeHost(c->h_h2d_seq);
     }
@@ -711,7 +769,7 @@ int64_t nerf_launch_count(const nerf_ctx *c) { return c ? c->launch_count : 0; }
 int nerf_set_weights(nerf_ctx *c, const float *flat, int64_t n) {
     if (!c || !flat) return NERF_ERR_INVALID_ARG;
     if (n != c->g.n_params) return fail(c, NERF_ERR_INVALID_ARG, "set_weights: wrong parameter count");
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaMemcpyAsync(c->d_params, flat, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->weights_dirty = true;
@@ -720,7 +778,7 @@ int nerf_set_weights(nerf_ctx *c, const float *flat, int64_t n) {
 static int get_blob(nerf_ctx *c, const float *src, float *dst, int64_t n) {
     if (!c || !dst) return NERF_ERR_INVALID_ARG;
     if (n != c->g.n_params) return fail(c, NERF_ERR_INVALID_ARG, "wrong parameter count");
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     return NERF_OK;
@@ -738,7 +796,7 @@ int nerf_get_adam_state(nerf_ctx *c, float *m, float *v, int64_t n, int64_t *ste
 int nerf_set_adam_state(nerf_ctx *c, const float *m, const float *v, int64_t n, int64_t step) {
     if (!c || !m || !v || step < 0) return NERF_ERR_INVALID_ARG;
     if (n != c->g.n_params) return fail(c, NERF_ERR_INVALID_ARG, "set_adam_state: wrong parameter count");
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaMemcpyAsync(c->d_m, m, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_v, v, sizeof(float) * n, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
@@ -748,7 +806,7 @@ int nerf_set_adam_state(nerf_ctx *c, const float *m, const float *v, int64_t n, 
 
 int nerf_set_images(nerf_ctx *c, const float *rgba, int32_t n_views) {
     if (!c || !rgba || n_views < 1) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const size_t bytes = sizeof(float) * 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->d_images) { guard_free(c->d_images); c->d_images = nullptr; }
@@ -762,7 +820,7 @@ int nerf_set_images(nerf_ctx *c, const float *rgba, int32_t n_views) {
 
 int nerf_set_images_rgba8(nerf_ctx *c, const uint8_t *rgba8, int32_t n_views) {
     if (!c || !rgba8 || n_views < 1) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const size_t bytes = 4 * (size_t)n_views * c->cfg.image_w * c->cfg.image_h;
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->d_images) { guard_free(c->d_images); c->d_images = nullptr; }
@@ -776,7 +834,7 @@ int nerf_set_images_rgba8(nerf_ctx *c, const uint8_t *rgba8, int32_t n_views) {
 
 int nerf_set_view_angles(nerf_ctx *c, const float *yaw_pitch, int32_t n) {
     if (!c || !yaw_pitch || n < 1) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     std::vector<ViewPose> poses((size_t)n);
     for (int i = 0; i < n; ++i) make_pose(yaw_pitch[2 * i], yaw_pitch[2 * i + 1], poses[i]);
     if (c->d_poses) { CU(c, cudaStreamSynchronize(c->stream)); guard_free(c->d_poses); c->d_poses = nullptr; }
@@ -811,7 +869,7 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
                    int32_t randomize, uint64_t seed, float *out_points, float *out_t, float *out_gold, float *out_dirs,
                    int64_t *out_indices) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     if (!c->d_poses) return fail(c, NERF_ERR_STATE, "get_batch: call nerf_set_view_angles first");
     const int R = c->R, S = c->S;
     if (n_picks < 1 || n_picks > R || R % n_picks != 0)
@@ -882,14 +940,26 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
 
 int nerf_predict(nerf_ctx *c, int32_t train, float *out_rgba, float *out_sigma) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     return do_predict(c, train, out_rgba, out_sigma);
+}
+
+int nerf_get_predictions(nerf_ctx *c, float *out_rgba, float *out_sigma) {
+    if (!c || (!out_rgba && !out_sigma)) return NERF_ERR_INVALID_ARG;
+    ENTER(c);
+    int rc = ensure_outputs(c);
+    if (rc) return rc;
+    if (out_rgba) CU(c, cudaMemcpyAsync(out_rgba, c->d_out, sizeof(float) * 4 * c->R, cudaMemcpyDeviceToHost, c->stream));
+    if (out_sigma) CU(c, cudaMemcpyAsync(out_sigma, c->d_sigma, sizeof(float) * c->B, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return NERF_OK;
 }
 
 int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points_floats, const float *distances,
                         int64_t n_distances, const float *dirs, int32_t train, float *out_rgba, float *out_sigma) {
     if (!c || !query_points || !distances) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    const bool pipelined = c->inputs_free;   // (before ENTER clears it)
+    ENTER(c);
     // assert_eq!(query_points.size(), [BATCH_SIZE*INDIM]); assert_eq!(distances.size(), [BATCH_SIZE]) (model.rs:162-163)
     if (n_points_floats != c->B * 3) return fail(c, NERF_ERR_INVALID_ARG, "predict: query_points must hold num_rays*num_samples*3 floats (model.rs:162)");
     if (n_distances != c->B) return fail(c, NERF_ERR_INVALID_ARG, "predict: distances must hold num_rays*num_samples floats (model.rs:163)");
@@ -909,38 +979,54 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
         if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->stream));
         return do_predict(c, train, out_rgba, out_sigma);
     }
-    if (!c->copy_stream) {
-        CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CU(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-        CU(c, cudaEventCreateWithFlags(&c->ev_dirs, cudaEventDisableTiming));
-        CU(c, cudaEventCreateWithFlags(&c->ev_all, cudaEventDisableTiming));
-        CU(c, guard_malloc(&c->d_h2d_flag, sizeof(unsigned int)));
-        CU(c, cudaMallocHost(&c->h_h2d_seq, sizeof(unsigned int) * kChunks));
-        for (int k = 0; k < kChunks; ++k) c->h_h2d_seq[k] = (unsigned int)k + 1u;
+    {
+        int rc0 = ensure_copy_stream(c);
+        if (rc0) return rc0;
     }
-    // everything enqueued so far (earlier readers of these buffers, the counter reset) precedes the copies
-    CU(c, cudaMemsetAsync(c->d_h2d_flag, 0, sizeof(unsigned int), c->stream));
+    // What the copies must wait for: the last reader of the batch inputs. Right after a single-launch nerf_step (whose loss read
+    // returned early) that is its compositing backward (ev_cbwd; dgrad, wgrad and Adam touch neither points, depths nor
+    // directions), so the next batch crosses PCIe under the rest of the previous step; otherwise everything enqueued so far.
+    if (pipelined) {
+        // The GPU still has the previous step's dgrad, weight gradients and Adam to run (~0.7 ms at the bench shape): the whole
+        // batch arrives before the forward kernel's turn comes, so it is three plain copies and the ordinary (non-polling) kernel.
+        CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_cbwd, 0));
+        if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->d_points, query_points, sizeof(float) * 3 * c->B, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaEventRecord(c->ev_all, c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_all, 0));
+        return do_predict(c, train, out_rgba, out_sigma);
+    }
+    unsigned int *const flag = c->d_h2d_flag + c->h2d_word;   // zero: reset in stream order after its previous use (below)
     CU(c, cudaEventRecord(c->ev_main, c->stream));
     CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_main, 0));
     if (dirs) CU(c, cudaMemcpyAsync(c->d_dirs, dirs, sizeof(float) * 3 * c->R, cudaMemcpyHostToDevice, c->copy_stream));
     CU(c, cudaEventRecord(c->ev_dirs, c->copy_stream));
     const int rays_per_chunk = (c->R + kChunks - 1) / kChunks;
     const int64_t chunk_samples = (int64_t)rays_per_chunk * c->S;
-    for (int k = 0; k < kChunks; ++k) {
-        const int64_t s0 = (int64_t)k * chunk_samples;
-        const int64_t ns = (c->B - s0 < chunk_samples) ? c->B - s0 : chunk_samples;
-        if (ns > 0) CU(c, cudaMemcpyAsync(c->d_points + 3 * s0, query_points + 3 * s0, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice, c->copy_stream));
-        CU(c, cudaMemcpyAsync(c->d_h2d_flag, c->h_h2d_seq + k, sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream));
-    }
-    CU(c, cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->copy_stream));   // compositing only
-    CU(c, cudaEventRecord(c->ev_all, c->copy_stream));
+    // The kernel is launched BEFORE the point copies are enqueued: its prologue waits for the counter anyway, and the ~20 driver
+    // calls below take the host longer (~50 us) than the first chunks take to cross PCIe -- launched last, the kernel started
+    // after half of the points had already arrived.
     CU(c, cudaStreamWaitEvent(c->stream, c->ev_dirs, 0));
-    c->h2d_flag_active = c->d_h2d_flag;
+    c->h2d_flag_active = flag;
     c->h2d_chunk_samples = chunk_samples;
     int rc = ensure_packed(c);
     if (rc == NERF_OK) rc = mlp_forward(c, 0, c->R, train ? 1 : 0);
     c->h2d_flag_active = nullptr;
-    cudaError_t e = cudaStreamWaitEvent(c->stream, c->ev_all, 0);   // (also on the error path: later work must not race the copies)
+    // the OTHER counter -- last used by the previous call's kernel, which precedes this point in the stream -- is reset for the
+    // next call
+    c->h2d_word ^= 1;
+    cudaError_t e = cudaMemsetAsync(c->d_h2d_flag + c->h2d_word, 0, sizeof(unsigned int), c->stream);
+    // (the copies are enqueued on the error path too: the counter must reach kChunks for a kernel that did get launched)
+    for (int k = 0; k < kChunks && e == cudaSuccess; ++k) {
+        const int64_t s0 = (int64_t)k * chunk_samples;
+        const int64_t ns = (c->B - s0 < chunk_samples) ? c->B - s0 : chunk_samples;
+        if (ns > 0) e = cudaMemcpyAsync(c->d_points + 3 * s0, query_points + 3 * s0, sizeof(float) * 3 * ns, cudaMemcpyHostToDevice, c->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(flag, c->h_h2d_seq + k, sizeof(unsigned int), cudaMemcpyHostToDevice, c->copy_stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_t, distances, sizeof(float) * c->B, cudaMemcpyHostToDevice, c->copy_stream);   // compositing only
+    if (e == cudaSuccess) e = cudaEventRecord(c->ev_all, c->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_all, 0);   // (later work must not race the copies)
     if (rc) return rc;
     if (e != cudaSuccess) return fail(c, NERF_ERR_CUDA, cudaGetErrorString(e));
     return do_predict(c, train, out_rgba, out_sigma, false, /*forward_done=*/true);
@@ -949,7 +1035,7 @@ int nerf_predict_points(nerf_ctx *c, const float *query_points, int64_t n_points
 int nerf_compositing(nerf_ctx *c, const float *densities, const float *colors, const float *distances, int32_t num_rays,
                      int32_t num_samples, float *out) {
     if (!c || !densities || !distances || !out) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     if (num_rays < 1 || num_samples < 1 || num_samples > 256) return fail(c, NERF_ERR_INVALID_ARG, "compositing: bad shape");
     const size_t n = (size_t)num_rays * num_samples;
     float *ds = nullptr, *dc = nullptr, *dd = nullptr, *dout = nullptr;
@@ -976,13 +1062,13 @@ int nerf_compositing(nerf_ctx *c, const float *densities, const float *colors, c
 
 int nerf_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     return do_step(c, gold, n_gold, loss);
 }
 
 int nerf_train_iter(nerf_ctx *c, uint64_t seed) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     if (!c->d_images && !c->d_images_u8) return fail(c, NERF_ERR_STATE, "train_iter: call nerf_set_images first");
     int n_picks = c->n_img_views < c->n_poses ? c->n_img_views : c->n_poses;
     while (n_picks > 1 && c->R % n_picks != 0) --n_picks;   // largest pick count that splits R evenly
@@ -995,7 +1081,7 @@ int nerf_train_iter(nerf_ctx *c, uint64_t seed) {
 
 int nerf_last_loss(nerf_ctx *c, float *loss) {
     if (!c || !loss) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaMemcpyAsync(c->h_loss, c->d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     *loss = *c->h_loss;
@@ -1004,7 +1090,7 @@ int nerf_last_loss(nerf_ctx *c, float *loss) {
 
 int nerf_sync(nerf_ctx *c) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->comm.p2p) {
         // the fused all-reduce + Adam kernel gives up on a peer that never publishes its gradient (instead of trapping or
@@ -1062,7 +1148,7 @@ static int render_rows_device(nerf_ctx *c, float yaw, float pitch, int32_t y0, i
 int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int32_t randomize, uint64_t seed, float *out_rgba,
                 uint32_t *out_0rgb) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const int W = c->cfg.image_w, H = c->cfg.image_h;
     if (y0 < 0 || y1 > H || y0 >= y1) return fail(c, NERF_ERR_INVALID_ARG, "render: bad row range");
     int rc = render_rows_device(c, yaw, pitch, y0, y1, randomize, seed, out_0rgb != nullptr);
@@ -1076,7 +1162,7 @@ int nerf_render(nerf_ctx *c, float yaw, float pitch, int32_t y0, int32_t y1, int
 
 int nerf_render_sharded(nerf_ctx *c, float yaw, float pitch, int32_t randomize, uint64_t seed, float *out_rgba, uint32_t *out_0rgb) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const int W = c->cfg.image_w, H = c->cfg.image_h, N = c->comm.nranks, r = c->comm.rank;
     if (H % N != 0) return fail(c, NERF_ERR_INVALID_ARG, "render_sharded: image height must divide evenly among the ranks");
     const int rows = H / N;
@@ -1100,11 +1186,15 @@ int nerf_render_sharded(nerf_ctx *c, float yaw, float pitch, int32_t randomize, 
 
 int nerf_log_metrics(nerf_ctx *c, const nerf_metrics *m) {
     if (!c || !m) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "log_metrics: no batch (call nerf_get_batch first)");
     const bool want_density = m->density_x || m->density_y || m->density_z || m->density_yx || m->density_zx || m->density_yz;
-    if ((want_density || m->prediction) && !c->outputs_valid)
-        return fail(c, NERF_ERR_STATE, "log_metrics: densities / predictions need nerf_predict (or a completed nerf_step / nerf_train_iter) on this batch");
+    if ((want_density || m->prediction) && !c->outputs_valid) {
+        if (!c->predicted || c->fwd_deferred)
+            return fail(c, NERF_ERR_STATE, "log_metrics: densities / predictions need nerf_predict (or a completed nerf_step / nerf_train_iter) on this batch");
+        int rc = ensure_outputs(c);
+        if (rc) return rc;
+    }
     if (!c->points_valid && !c->batch_poses) return fail(c, NERF_ERR_STATE, "log_metrics: batch has neither points nor ray records");
     const int W = c->cfg.image_w, H = c->cfg.image_h;
     // scratch layout (device): screen[W+H] u32 | t[2000] u32 | world[30000] u32 | pad | density_hist[6000] f64 | density keys[30000] u64 | prediction keys[W*H] u64 | resolved u32 [30000 + W*H]
@@ -1176,7 +1266,7 @@ int nerf_comm_unique_id(void *id128) {
 
 int nerf_comm_init_rank(nerf_ctx *c, const void *id128, int32_t rank, int32_t nranks) {
     if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     char eb[256] = {0};
     if (comm_init_rank(c->comm, id128, rank, nranks, eb, sizeof(eb))) return fail(c, NERF_ERR_COMM, eb);
     // peer-memory gradient exchange (fused all-reduce + Adam); NERF_B200_P2P=0 keeps the plain NCCL all-reduce
@@ -1203,13 +1293,13 @@ int nerf_comm_destroy(nerf_ctx *c) {
 
 int nerf_timer_start(nerf_ctx *c) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaEventRecord(c->t0, c->stream));
     return NERF_OK;
 }
 int nerf_timer_stop(nerf_ctx *c, float *ms) {
     if (!c || !ms) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     CU(c, cudaEventRecord(c->t1, c->stream));
     CU(c, cudaEventSynchronize(c->t1));
     CU(c, cudaEventElapsedTime(ms, c->t0, c->t1));
@@ -1218,7 +1308,7 @@ int nerf_timer_stop(nerf_ctx *c, float *ms) {
 
 int nerf_profile_enable(nerf_ctx *c, int32_t on) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     c->prof.collect(c->stream);
     c->prof.reset();
     c->prof.on = on != 0;
@@ -1226,7 +1316,7 @@ int nerf_profile_enable(nerf_ctx *c, int32_t on) {
 }
 int nerf_profile_read(nerf_ctx *c, char *names, float *total_ms, int32_t *launches, int32_t capacity, int32_t *count) {
     if (!c || !count) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     c->prof.collect(c->stream);
     const int n = (int)c->prof.names.size();
     *count = n;
@@ -1240,7 +1330,7 @@ int nerf_profile_read(nerf_ctx *c, char *names, float *total_ms, int32_t *launch
 
 int nerf_flush_l2(nerf_ctx *c) {
     if (!c) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     if (!c->d_flush) {
         c->flush_bytes = (size_t)256 << 20;  // 2x the 126 MB L2
         CU(c, guard_malloc(&c->d_flush, c->flush_bytes));
@@ -1375,7 +1465,7 @@ int nerf_debug_check_guards(int32_t *n_allocations) {
 int nerf_debug_read_panel(nerf_ctx *c, int32_t area, int32_t tile, int32_t slot, void *out) {
     if (!c || !out) return NERF_ERR_INVALID_ARG;
     if (!c->tc) return fail(c, NERF_ERR_STATE, "debug_read_panel: not a tcgen05 context");
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const int rc = tc_debug_read(c->tc, area, tile, slot, out, c->stream);
     if (rc == -1) return fail(c, NERF_ERR_INVALID_ARG, "debug_read_panel: bad area/tile/slot");
     if (rc) return fail(c, NERF_ERR_CUDA, "debug_read_panel: copy failed");
@@ -1386,7 +1476,7 @@ int nerf_debug_trace(nerf_ctx *c, int32_t program, uint64_t *out) {
     if (!c || !out) return NERF_ERR_INVALID_ARG;
     if (!c->tc) return fail(c, NERF_ERR_STATE, "debug_trace: not a tcgen05 context");
     if (!c->batch_valid) return fail(c, NERF_ERR_STATE, "debug_trace: no batch");
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     int rc = ensure_packed(c);
     if (rc) return rc;
     const int nr = c->chunk < c->R ? c->chunk : c->R;
@@ -1400,7 +1490,7 @@ int nerf_debug_trace(nerf_ctx *c, int32_t program, uint64_t *out) {
 // (pick sizes whose working set exceeds the 126 MB L2 so every launch streams HBM). CUDA events on the context's stream.
 int nerf_debug_bench_stage(nerf_ctx *c, int32_t stage, int32_t num_rays, int32_t num_samples, int32_t iters, float *ms_per_launch) {
     if (!c || !ms_per_launch || num_rays < 1 || num_samples < 1 || num_samples > 256 || iters < 1) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const int64_t n = (int64_t)num_rays * num_samples;
     std::vector<void *> bufs;
     auto alloc = [&](size_t bytes) -> void * {
@@ -1503,7 +1593,7 @@ int nerf_debug_bench_stage(nerf_ctx *c, int32_t stage, int32_t num_rays, int32_t
 
 int nerf_debug_wgrad_marks(nerf_ctx *c, uint64_t *out, int32_t capacity_ctas) {
     if (!c || !out || !c->tc) return NERF_ERR_INVALID_ARG;
-    CU(c, cudaSetDevice(c->device));
+    ENTER(c);
     const int n = tc_debug_wgrad_marks(c->tc, reinterpret_cast<unsigned long long *>(out), capacity_ctas, c->stream);
     if (n < 0) return fail(c, NERF_ERR_INVALID_ARG, "wgrad_marks: capacity too small or copy failed");
     return n;

@@ -83,12 +83,41 @@ class NeRF {
                                                               const std::vector<float> &distances,
                                                               const std::vector<float> *dirs = nullptr, bool train = true) {
         std::vector<float> out((size_t)cfg_.num_rays * 4), sig((size_t)cfg_.num_rays * cfg_.num_samples);
+        ++pred_gen_;
         check(ctx_, nerf_predict_points(ctx_, query_points.data(), (int64_t)query_points.size(), distances.data(),
                                         (int64_t)distances.size(), dirs ? dirs->data() : nullptr, train ? 1 : 0, out.data(), sig.data()));
         return {std::move(out), std::move(sig)};
     }
+    // The prediction as the reference has it: a device tensor (main.rs:58). Enqueues the forward and returns without a device
+    // synchronisation; Trainer::step(Prediction, gold) consumes it, pixels() / densities() fetch the values on demand.
+    struct Prediction {
+        NeRF *model;
+        uint64_t gen;
+        std::vector<float> pixels() const {
+            model->check_current(gen);
+            std::vector<float> out((size_t)model->cfg_.num_rays * 4);
+            check(model->ctx_, nerf_get_predictions(model->ctx_, out.data(), nullptr));
+            return out;
+        }
+        std::vector<float> densities() const {
+            model->check_current(gen);
+            std::vector<float> sig((size_t)model->cfg_.num_rays * model->cfg_.num_samples);
+            check(model->ctx_, nerf_get_predictions(model->ctx_, nullptr, sig.data()));
+            return sig;
+        }
+    };
+    Prediction predict_device(const std::vector<float> &query_points, const std::vector<float> &distances,
+                              const std::vector<float> *dirs = nullptr, bool train = true) {
+        check(ctx_, nerf_predict_points(ctx_, query_points.data(), (int64_t)query_points.size(), distances.data(),
+                                        (int64_t)distances.size(), dirs ? dirs->data() : nullptr, train ? 1 : 0, nullptr, nullptr));
+        return Prediction{this, ++pred_gen_};
+    }
+    void check_current(uint64_t gen) const {
+        if (gen != pred_gen_) throw Error(NERF_ERR_STATE, "stale prediction handle: the model has run another predict since");
+    }
     std::vector<float> predict_resident(bool train = true) {
         std::vector<float> out((size_t)cfg_.num_rays * 4);
+        ++pred_gen_;
         check(ctx_, nerf_predict(ctx_, train ? 1 : 0, out.data(), nullptr));
         return out;
     }
@@ -158,6 +187,7 @@ class NeRF {
     nerf_config cfg_;
     nerf_ctx *ctx_ = nullptr;
     int n_views_ = 0;
+    uint64_t pred_gen_ = 0;   // bumped by every predict: older Prediction handles become stale
 };
 
 // compositing(&densities [R,S], colors [R,S,4], distances [R,S]) -> [R,4]  (model.rs:234)
@@ -172,6 +202,13 @@ inline std::vector<float> compositing(NeRF &m, const std::vector<float> &densiti
 class Trainer {  // Trainer::new(&vs, lr) / step (model.rs:301-325)
    public:
     explicit Trainer(NeRF &m) : m_(m) {}
+    float step(const NeRF::Prediction &prediction, const std::vector<float> &gold, size_t /*iter*/ = 0) {
+        if (prediction.model != &m_) throw Error(NERF_ERR_INVALID_ARG, "the prediction belongs to another model");
+        m_.check_current(prediction.gen);
+        float loss = 0.f;
+        check(m_.ctx(), nerf_step(m_.ctx(), gold.data(), (int64_t)gold.size(), &loss));
+        return loss;
+    }
     float step(const std::vector<float> &predictions, const std::vector<float> &gold, size_t /*iter*/ = 0) {
         if (predictions.size() != (size_t)m_.config().num_rays * 4) throw Error(NERF_ERR_INVALID_ARG, "predictions must be [NUM_RAYS, LABELS]");
         float loss = 0.f;

@@ -18,6 +18,7 @@ LINK = ["-L", LIBDIR, "-lnerf_b200", f"-Wl,-rpath,{LIBDIR}", "-L/usr/local/cuda/
 
 SRC = r'''
 #include "nerf_rs_b200/csrc/host/nerf_b200.hpp"
+#include <cmath>
 #include <cstdio>
 int main() {
     auto angles = nerf::get_view_angles(6);
@@ -30,7 +31,19 @@ int main() {
         auto batch = nerf::get_multiview_batch(model, rng);
         nerf::Trainer trainer(model);
         auto log = model.log_metrics(false, false);          // logging.rs:13-107 on the device
-        (void)batch; (void)trainer; (void)log;
+        // the prediction as a device handle (main.rs:58 -> :72): step consumes it, the pixels come on demand
+        auto &[indices, qp, dist, gold] = batch;
+        std::vector<float> dirs((size_t)model.config().num_rays * 3, 0.f);
+        for (size_t i = 2; i < dirs.size(); i += 3) dirs[i] = -1.f;
+        auto pred = model.predict_device(qp, dist, &dirs);
+        auto px_before = pred.pixels();
+        float loss = trainer.step(pred, gold);
+        auto px_after = pred.pixels();                          // (the compositing backward rewrote the same pixels)
+        if (!(loss > 0.f) || px_before.size() != gold.size()) return 5;
+        for (size_t i = 0; i < px_before.size(); ++i) if (std::fabs(px_before[i] - px_after[i]) > 1e-5f) return 6;
+        auto eager = model.predict(qp, dist, &dirs);
+        try { pred.pixels(); return 7; } catch (const nerf::Error &e) { if (e.status != NERF_ERR_STATE) return 8; }   // stale handle
+        (void)indices; (void)log; (void)eager;
     } catch (const nerf::Error &e) {
         std::printf("status %d\n", e.status);
         return e.status == NERF_ERR_NO_DEVICE ? 0 : 3;

@@ -176,6 +176,60 @@ def test_overlapped_host_copy_equals_plain_copy():
     assert np.allclose(res[0][2], res[1][2], rtol=1e-3, atol=1e-6 * np.abs(res[1][2]).max())   # (wgrad atomics are unordered)
 
 
+def test_device_resident_prediction_equals_eager_predict():
+    """predict(lazy=True) keeps the prediction on the device like the reference's Tensor (main.rs:58 -> :72): compositing is left
+    to the step (or to the first read), Trainer.step consumes the handle, and pixels, densities, loss, gradients and updated
+    weights are the eager path's bit for bit (deterministic weight gradients, so the comparison can be exact)."""
+    cfg = nb.default_config(image_w=64, image_h=64, num_rays=100, num_samples=50, hidden=128, deterministic_grads=1)
+    pts, t, dirs, gold = G.make_points(100, 50, 9)
+    w0 = M.flatten_params(M.init_params(G.model_cfg(cfg), 0)).numpy()
+
+    def run(lazy, read_before_step):
+        m = nb.NeRF(cfg)
+        m.set_weights(w0)
+        tr = nb.Trainer(m)
+        if lazy:
+            pred, none = m.predict(pts, t, dirs.reshape(-1), train=True, lazy=True)
+            assert none is None and isinstance(pred, nb.Prediction) and pred.shape == (100, 4)
+            px0 = pred.numpy() if read_before_step else None
+            loss = tr.step(pred, gold)
+            px, sig = np.asarray(pred), pred.densities()      # after the step: the compositing backward rewrote the same pixels
+            if px0 is not None:
+                assert np.allclose(px0, px, rtol=0, atol=1e-6)
+            m.predict(pts, t, dirs.reshape(-1), train=True, lazy=True)
+            with pytest.raises(nb.NerfError):
+                pred.numpy()                                    # stale handle
+            with pytest.raises(nb.NerfError):
+                tr.step(pred, gold)
+        else:
+            px, sig = m.predict(pts, t, dirs.reshape(-1), train=True)
+            loss = tr.step(px, gold)
+        return px, sig, loss, m.get_grads(), m.get_weights()
+
+    eager = run(False, False)
+    for read_first in (False, True):
+        lazy = run(True, read_first)
+        assert np.allclose(lazy[0], eager[0], rtol=0, atol=1e-6) and np.array_equal(lazy[1], eager[1])
+        assert lazy[2] == eager[2]
+        assert np.array_equal(lazy[3], eager[3]) and np.array_equal(lazy[4], eager[4])
+    # resident batch: a deferred prediction is also what log_metrics' density / prediction maps read
+    m = nb.NeRF(nb.default_config(image_w=64, image_h=64, num_rays=128, num_samples=32, hidden=64))
+    m.set_images(_sphere_images(4, 64, 64))
+    m.set_view_angles(nb.get_view_angles(6)[:4])
+    m.get_batch(None, None, 4, None, True, 3, want=())
+    pred, _ = m.predict(train=True, lazy=True)
+    logs = m.log_metrics(True, True)
+    px = pred.numpy()
+    m2 = nb.NeRF(nb.default_config(image_w=64, image_h=64, num_rays=128, num_samples=32, hidden=64))
+    m2.set_weights(m.get_weights())
+    m2.set_images(_sphere_images(4, 64, 64))
+    m2.set_view_angles(nb.get_view_angles(6)[:4])
+    m2.get_batch(None, None, 4, None, True, 3, want=())
+    px2, _ = m2.predict(train=True)
+    logs2 = m2.log_metrics(True, True)
+    assert np.array_equal(px, px2) and np.array_equal(logs["prediction"], logs2["prediction"]) and np.array_equal(logs["density_yx"], logs2["density_yx"])
+
+
 def test_full_size_properties():
     """BASELINE configs[1] at full size (800x800 views, 4096 rays x 64 samples, W=256): size-independent properties instead of
     a CPU comparison -- (1) the fused-sampling forward equals the forward on the sampler's own points, bit for bit;
