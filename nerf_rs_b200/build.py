@@ -18,7 +18,8 @@ def _stale():
         return True
     t = os.path.getmtime(OUT)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", f) for f in os.listdir(os.path.join(HERE, "..", "include"))]
-    return any(os.path.getmtime(d) > t for d in deps)
+    # (files only: a directory's mtime changes whenever the tree is copied, which would rebuild on every fresh box)
+    return any(os.path.isfile(d) and os.path.getmtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
@@ -44,7 +45,7 @@ def build(force=False, verbose=False):
             f.write(out)
     if failed:
         raise RuntimeError("nvcc build failed")
-    cmd = ["nvcc", "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl", "-lz"]
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl", "-lz"]
     subprocess.check_call(cmd)
     return OUT
 
