@@ -147,6 +147,7 @@ struct nerf_ctx {
     cudaEvent_t ev_cbwd = nullptr;        // recorded after a step's compositing backward: the loss is final, the batch inputs have no reader left
     bool inputs_free = false;             // the last enqueuing API call was a single-launch nerf_step (ev_cbwd covers every reader of the inputs)
     int h2d_word = 0;                     // which of the two arrival counters the next overlapped copy uses
+    bool sample_side = false;             // nerf_train_iter: this batch's sampler may run on the copy stream behind ev_cbwd
     unsigned int *d_h2d_flag = nullptr, *h_h2d_seq = nullptr;   // two device counters (alternating per call); pinned 1, 2, 3, ... source values
     const unsigned int *h2d_flag_active = nullptr;               // non-NULL while the resident points are still arriving
     int64_t h2d_chunk_samples = 0;
@@ -579,8 +580,20 @@ int run_sampler(nerf_ctx *c, int nr, const int32_t *view_pick, int rays_per_pick
     a.t = c->d_t;
     a.points = write_points ? c->d_points : nullptr;
     a.gold = c->d_gold;
-    Scope s(c, "sample");
-    launch_sample(a, c->num_sms, c->stream);
+    // A fused iteration that follows another one: everything the sampler writes (picks, ray records, depths, gold) had its
+    // last reader in the previous step's compositing backward, and nothing it reads depends on the weights -- it runs on the
+    // copy stream behind that kernel's event, under the previous step's dgrad / weight gradients / gradient exchange, instead
+    // of between Adam and the forward. (Not while profiling: the per-kernel events are recorded on the main stream.)
+    const bool side = c->sample_side && !c->prof.on && c->copy_stream;
+    if (side) CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_cbwd, 0));
+    {
+        Scope s(c, "sample");
+        launch_sample(a, c->num_sms, side ? c->copy_stream : c->stream);
+    }
+    if (side) {
+        CU(c, cudaEventRecord(c->ev_all, c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_all, 0));
+    }
     return check_launch(c, "sample");
 }
 
@@ -1068,11 +1081,17 @@ int nerf_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
 
 int nerf_train_iter(nerf_ctx *c, uint64_t seed) {
     if (!c) return NERF_ERR_INVALID_ARG;
+    static const bool no_side = getenv("NERF_B200_NO_SAMPLER_OVERLAP") != nullptr;   // A/B
+    const bool after_step = c->inputs_free && !no_side;   // (before ENTER clears it) the previous call was a single-launch step
     ENTER(c);
     if (!c->d_images && !c->d_images_u8) return fail(c, NERF_ERR_STATE, "train_iter: call nerf_set_images first");
     int n_picks = c->n_img_views < c->n_poses ? c->n_img_views : c->n_poses;
     while (n_picks > 1 && c->R % n_picks != 0) --n_picks;   // largest pick count that splits R evenly
-    int rc = nerf_get_batch(c, nullptr, nullptr, n_picks, nullptr, 1, seed, nullptr, nullptr, nullptr, nullptr, nullptr);
+    int rc = ensure_copy_stream(c);   // (so that every step records ev_cbwd)
+    if (rc) return rc;
+    c->sample_side = after_step;
+    rc = nerf_get_batch(c, nullptr, nullptr, n_picks, nullptr, 1, seed, nullptr, nullptr, nullptr, nullptr, nullptr);
+    c->sample_side = false;
     if (rc) return rc;
     rc = do_predict(c, 1, nullptr, nullptr, /*skip_composite=*/true);
     if (rc) return rc;
