@@ -882,8 +882,15 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
                    int32_t randomize, uint64_t seed, float *out_points, float *out_t, float *out_gold, float *out_dirs,
                    int64_t *out_indices) {
     if (!c) return NERF_ERR_INVALID_ARG;
+    // Directly after a single-launch nerf_step every buffer this call writes had its last reader in that step's compositing
+    // backward: the host inputs, the sampler and the read-back then go through the copy stream behind that kernel's event
+    // instead of queueing behind dgrad, weight gradients and Adam on the main stream (nerf_train_iter asks for the same).
+    static const bool no_side = getenv("NERF_B200_NO_SAMPLER_OVERLAP") != nullptr;   // A/B
+    const bool side = (c->sample_side || (c->inputs_free && !no_side)) && c->copy_stream && !c->prof.on;
     ENTER(c);
     if (!c->d_poses) return fail(c, NERF_ERR_STATE, "get_batch: call nerf_set_view_angles first");
+    cudaStream_t st = side ? c->copy_stream : c->stream;
+    if (side) CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_cbwd, 0));
     const int R = c->R, S = c->S;
     if (n_picks < 1 || n_picks > R || R % n_picks != 0)
         return fail(c, NERF_ERR_INVALID_ARG, "get_batch: can't divide rays evenly among views (dataset.rs:73-81)");
@@ -904,7 +911,7 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
             c->h_i32[2 * i] = (int32_t)y;
             c->h_i32[2 * i + 1] = (int32_t)x;
         }
-        CU(c, cudaMemcpyAsync(c->d_pix, c->h_i32, sizeof(int32_t) * 2 * R, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_pix, c->h_i32, sizeof(int32_t) * 2 * R, cudaMemcpyHostToDevice, st));
     }
     if (view_index) {
         rc = ensure_i32(c, (size_t)2 * R + n_picks);
@@ -913,10 +920,10 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
             if (view_index[i] < 0 || view_index[i] >= n_views) return fail(c, NERF_ERR_INVALID_ARG, "get_batch: view index out of range");
             c->h_i32[2 * R + i] = (int32_t)view_index[i];
         }
-        CU(c, cudaMemcpyAsync(c->d_view_pick, c->h_i32 + 2 * R, sizeof(int32_t) * n_picks, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_view_pick, c->h_i32 + 2 * R, sizeof(int32_t) * n_picks, cudaMemcpyHostToDevice, st));
     }
     if (indices_yx || view_index) {
-        CU(c, cudaEventRecord(c->ev_stage, c->stream));
+        CU(c, cudaEventRecord(c->ev_stage, st));
         c->stage_busy = true;
     }
     c->gen_pix = indices_yx ? 0 : 1;       // missing picks are drawn inside the sampler (Philox)
@@ -924,29 +931,32 @@ int nerf_get_batch(nerf_ctx *c, const int64_t *indices_yx, const int64_t *view_i
     c->pick_views = n_views;
     const float *dj = nullptr;
     if (jitter && randomize) {
-        CU(c, cudaMemcpyAsync(c->d_jitter, jitter, sizeof(float) * (size_t)R * S, cudaMemcpyHostToDevice, c->stream));
+        CU(c, cudaMemcpyAsync(c->d_jitter, jitter, sizeof(float) * (size_t)R * S, cudaMemcpyHostToDevice, st));
         dj = c->d_jitter;
     }
     const int64_t ray_base = (int64_t)c->comm.rank * R;
+    const bool side_was = c->sample_side;
+    c->sample_side = side;
     rc = run_sampler(c, R, c->d_view_pick, R / n_picks, c->d_poses, 0, dj, randomize, seed, ray_base, c->d_images != nullptr || c->d_images_u8 != nullptr,
                      out_points != nullptr);
+    c->sample_side = side_was;
     if (rc) return rc;
     c->batch_valid = true;
     c->predicted = false;
     c->outputs_valid = false;
     c->acts_valid = false;
     bool sync = false;
-    if (out_points) { CU(c, cudaMemcpyAsync(out_points, c->d_points, sizeof(float) * 3 * c->B, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
-    if (out_t) { CU(c, cudaMemcpyAsync(out_t, c->d_t, sizeof(float) * c->B, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
-    if (out_gold) { CU(c, cudaMemcpyAsync(out_gold, c->d_gold, sizeof(float) * 4 * R, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
-    if (out_dirs) { CU(c, cudaMemcpyAsync(out_dirs, c->d_dirs, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, c->stream)); sync = true; }
+    if (out_points) { CU(c, cudaMemcpyAsync(out_points, c->d_points, sizeof(float) * 3 * c->B, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (out_t) { CU(c, cudaMemcpyAsync(out_t, c->d_t, sizeof(float) * c->B, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (out_gold) { CU(c, cudaMemcpyAsync(out_gold, c->d_gold, sizeof(float) * 4 * R, cudaMemcpyDeviceToHost, st)); sync = true; }
+    if (out_dirs) { CU(c, cudaMemcpyAsync(out_dirs, c->d_dirs, sizeof(float) * 3 * R, cudaMemcpyDeviceToHost, st)); sync = true; }
     if (out_indices) {
         rc = ensure_i32(c, (size_t)2 * R + n_picks);
         if (rc) return rc;
-        CU(c, cudaMemcpyAsync(c->h_i32, c->d_pix, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaMemcpyAsync(c->h_i32, c->d_pix, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, st));
         sync = true;
     }
-    if (sync) CU(c, cudaStreamSynchronize(c->stream));
+    if (sync) CU(c, cudaStreamSynchronize(st));
     if (out_indices) for (int i = 0; i < 2 * R; ++i) out_indices[i] = c->h_i32[i];
     return check_launch(c, "get_batch");
 }
