@@ -29,7 +29,8 @@
 extern "C" {
 #endif
 
-#define NERF_B200_ABI_VERSION 1
+/* 2: nerf_config.deterministic_grads, nerf_get_predictions, NERF_MLP_TCGEN05_SS (round 2); nerf_step returns when the loss is final */
+#define NERF_B200_ABI_VERSION 2
 
 /* status codes */
 #define NERF_OK 0

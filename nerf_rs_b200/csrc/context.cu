@@ -5,6 +5,7 @@
 // (tcgen05 chain kernels or the SIMT cross-check) and one CUDA stream on which everything
 // is enqueued. Call surface mirrors src/main.rs:57-72:
 //   get_multiview_batch -> NeRF::predict -> (compositing) -> Trainer::step.
+#include <nvtx3/nvToolsExt.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -174,13 +175,19 @@ int fail(nerf_ctx *c, int code, const std::string &msg) {
         (c)->inputs_free = false;                 \
     } while (0)
 
+// One Scope per kernel (group) launch: counts it, times it with CUDA events when profiling is on (nerf_profile_enable), and
+// opens an NVTX range of the same name (header-only NVTX3: a no-op unless a tool such as Nsight Systems is attached).
 struct Scope {
     nerf_ctx *c;
     Scope(nerf_ctx *c_, const char *name, int launches = 1) : c(c_) {
         c->launch_count += launches;
+        nvtxRangePushA(name);
         c->prof.begin(name, c->stream);
     }
-    ~Scope() { c->prof.end(c->stream); }
+    ~Scope() {
+        c->prof.end(c->stream);
+        nvtxRangePop();
+    }
 };
 
 int check_launch(nerf_ctx *c, const char *what) {

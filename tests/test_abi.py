@@ -29,7 +29,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.nerf_abi_version() == 1
+    assert lib.nerf_abi_version() == 2
 
 
 def test_config_struct_matches_header():
