@@ -230,6 +230,26 @@ def test_device_resident_prediction_equals_eager_predict():
     assert np.array_equal(px, px2) and np.array_equal(logs["prediction"], logs2["prediction"]) and np.array_equal(logs["density_yx"], logs2["density_yx"])
 
 
+def test_overlapped_paths_equal_the_single_stream_run():
+    """tests/pipeline_worker.py: a mixed sequence of device-resident / eager predictions, host-index batches and fused iterations
+    with pinned buffers rewritten between calls gives the same bits whether copies, sampler and the loss read overlap the
+    previous step (as shipped) or everything runs on one stream and every step is waited for."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for serial in (False, True):
+        env = dict(os.environ)
+        if serial:
+            env.update(NERF_B200_STEP_SYNC="1", NERF_B200_NO_SAMPLER_OVERLAP="1", NERF_B200_NO_H2D_OVERLAP="1")
+        p = subprocess.run([sys.executable, os.path.join(root, "tests", "pipeline_worker.py")], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+        line = [l for l in p.stdout.splitlines() if l.startswith("DIGEST")][-1]
+        print(("serial   " if serial else "overlap  ") + line)
+        outs.append(line)
+    assert outs[0] == outs[1]
+
+
 def test_full_size_properties():
     """BASELINE configs[1] at full size (800x800 views, 4096 rays x 64 samples, W=256): size-independent properties instead of
     a CPU comparison -- (1) the fused-sampling forward equals the forward on the sampler's own points, bit for bit;
