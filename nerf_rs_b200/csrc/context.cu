@@ -548,7 +548,8 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         *loss = l;
     }
     rc = check_launch(c, "step");
-    c->inputs_free = rc == NERF_OK && cbwd_recorded;
+    // (a micro-batched step re-runs the forward -- which reads the batch inputs -- after the compositing backward)
+    c->inputs_free = rc == NERF_OK && cbwd_recorded && c->chunk >= c->R;
     return rc;
 }
 

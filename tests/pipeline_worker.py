@@ -14,7 +14,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nerf_rs_b200 as nb  # noqa: E402
 
 R, S, W = 512, 64, 64
-cfg = nb.default_config(image_w=W, image_h=W, num_rays=R, num_samples=S, hidden=128, deterministic_grads=1)
+CHUNK = int(os.environ.get("PIPELINE_WORKER_CHUNK", "0"))   # > 0: micro-batched steps (the forward re-runs inside nerf_step)
+cfg = nb.default_config(image_w=W, image_h=W, num_rays=R, num_samples=S, hidden=128, deterministic_grads=1, max_rays_per_launch=CHUNK)
 m = nb.NeRF(cfg)
 rng = np.random.default_rng(5)
 imgs = rng.random((4, W * W, 4)).astype(np.float32)

@@ -230,8 +230,10 @@ def test_device_resident_prediction_equals_eager_predict():
     assert np.array_equal(px, px2) and np.array_equal(logs["prediction"], logs2["prediction"]) and np.array_equal(logs["density_yx"], logs2["density_yx"])
 
 
-def test_overlapped_paths_equal_the_single_stream_run():
-    """tests/pipeline_worker.py: a mixed sequence of device-resident / eager predictions, host-index batches and fused iterations
+@pytest.mark.parametrize("chunk", [0, 128])
+def test_overlapped_paths_equal_the_single_stream_run(chunk):
+    """tests/pipeline_worker.py (chunk > 0: micro-batched steps, which re-run the forward after the compositing backward and
+    must therefore NOT release the batch inputs early): a mixed sequence of device-resident / eager predictions, host-index batches and fused iterations
     with pinned buffers rewritten between calls gives the same bits whether copies, sampler and the loss read overlap the
     previous step (as shipped) or everything runs on one stream and every step is waited for."""
     import subprocess
@@ -239,7 +241,7 @@ def test_overlapped_paths_equal_the_single_stream_run():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     outs = []
     for serial in (False, True):
-        env = dict(os.environ)
+        env = dict(os.environ, PIPELINE_WORKER_CHUNK=str(chunk))
         if serial:
             env.update(NERF_B200_STEP_SYNC="1", NERF_B200_NO_SAMPLER_OVERLAP="1", NERF_B200_NO_H2D_OVERLAP="1")
         p = subprocess.run([sys.executable, os.path.join(root, "tests", "pipeline_worker.py")], cwd=root, env=env, capture_output=True, text=True, timeout=600)
