@@ -461,6 +461,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
     CU(c, cudaMemsetAsync(gacc, 0, sizeof(float) * c->g.n_params, c->stream));   // (before the kernels, so that they stay back to back for the programmatic launches)
     int rc = NERF_OK;
     bool cbwd_recorded = false;
+    bool fwd_in_step = false;   // a forward ran inside this step (micro-batches, or a step after an inference predict): it reads the batch inputs
     if (!c->fwd_deferred) {
         rc = composite_backward(0, c->R);
         if (rc) return rc;
@@ -476,6 +477,7 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         if (!c->acts_valid) {
             rc = mlp_forward(c, r0, nr, 1);  // (re)compute this micro-batch's activations
             if (rc) return rc;
+            fwd_in_step = true;
         }
         if (c->fwd_deferred) {
             rc = composite_backward(r0, nr);
@@ -548,8 +550,8 @@ int do_step(nerf_ctx *c, const float *gold, int64_t n_gold, float *loss) {
         *loss = l;
     }
     rc = check_launch(c, "step");
-    // (a micro-batched step re-runs the forward -- which reads the batch inputs -- after the compositing backward)
-    c->inputs_free = rc == NERF_OK && cbwd_recorded && c->chunk >= c->R;
+    // (a step that re-runs the forward -- which reads the batch inputs -- after the compositing backward does not release them)
+    c->inputs_free = rc == NERF_OK && cbwd_recorded && !fwd_in_step && c->chunk >= c->R;
     return rc;
 }
 

@@ -46,8 +46,8 @@ for it in range(12):
         gold[:] = np.clip(gold * np.float32(0.999), 0, 1)
         if it % 8 == 0:
             digest(pred.numpy(), pred.densities())
-    elif mode == 1:   # eager prediction straight after a step
-        out, sig = m.predict(pts, tt, dirs, train=True)
+    elif mode == 1:   # eager prediction straight after a step (once as an inference predict: the step then re-runs the forward itself)
+        out, sig = m.predict(pts, tt, dirs, train=(it != 5))
         losses.append(tr.step(out, gold))
         digest(out, sig)
     elif mode == 2:   # host indices / jitter straight after a step, gold read back, resident predict
