@@ -28,7 +28,9 @@ W_IMG, R, S, PICKS, HIDDEN = 64, 512, 32, 4, 128
 
 def make(p2p):
     os.environ["NERF_B200_P2P"] = "1" if p2p else "0"
-    cfg = nb.default_config(image_w=W_IMG, image_h=W_IMG, num_rays=R, num_samples=S, hidden=HIDDEN)
+    # (deterministic weight gradients: without them the unordered atomics of 20 Adam steps amplify into a 1e-3..5e-3 difference
+    #  between ANY two runs, which says nothing about the exchange paths being compared below)
+    cfg = nb.default_config(image_w=W_IMG, image_h=W_IMG, num_rays=R, num_samples=S, hidden=HIDDEN, deterministic_grads=1)
     m = nb.NeRF(cfg, device=local)
     mcfg = G.model_cfg(cfg)
     params_t = M.init_params(mcfg, 0)
@@ -115,7 +117,7 @@ for p2p in (True, False):
 dw = np.abs(res[True][0] - res[False][0]).max() / np.abs(res[False][0]).max()
 if rank == 0:
     print(f"peer-memory vs NCCL exchange after 20 steps: max |dw| / max |w| = {dw:.2e}")
-assert dw < 5e-3
+assert dw < 1e-3   # (the two paths differ only in the order the ranks' gradients are summed in: nothing at 2 ranks)
 dist.barrier()
 if rank == 0:
     print("DP_CHECK_OK")
